@@ -1,0 +1,22 @@
+# Builds zk_b200/libzk_b200.so (C ABI in include/zk_b200.h) for sm_100a, in tree.
+NVCC ?= nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := -std=c++17 -O3 -lineinfo $(ARCH) -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v
+SRC := zk_b200/csrc
+OBJDIR := build
+OBJS := $(OBJDIR)/api.o $(OBJDIR)/kernels_sumcheck.o $(OBJDIR)/kernels_mle.o $(OBJDIR)/kernels_ntt.o $(OBJDIR)/microbench.o
+HDRS := $(SRC)/field.cuh $(SRC)/kernels.h $(SRC)/host_field.hpp $(SRC)/keccak.hpp include/zk_b200.h
+
+all: zk_b200/libzk_b200.so
+
+$(OBJDIR)/%.o: $(SRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
+
+zk_b200/libzk_b200.so: $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -Xlinker --version-script=$(SRC)/exports.map -lcudart_static -ldl -lpthread -lrt
+
+clean:
+	rm -rf $(OBJDIR) zk_b200/libzk_b200.so
+
+.PHONY: all clean

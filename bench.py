@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — sumcheck prove throughput (field-mul/s) and prove time on B200, BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (CUDA path through the C ABI)
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's CPU algorithm (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU, NCCL
+
+Workload (config.workload): BASELINE config 3 — degree-3 product sumcheck (3 factor tables, MAX_VAR_DEGREE = 3),
+`prove_partial`, BLS12-381 Fr, synthetic seeded tables.  N = 1: 2^26 entries per table (6 GiB, larger than L2).
+N > 1: weak scaling, 2^26 entries per GPU (2^(26+log2 N) total; `--log-n 30` gives BASELINE config 4 exactly),
+tables sharded by the last-bound variables, round polynomials all-reduced over NCCL.
+
+A step = one whole proof.  `value` = ALG_MULS / prove time with tables resident in HBM (tables are
+regenerated on the device between steps, outside the timed region, because prove consumes them);
+ALG_MULS(n,m,D) = ((D+1)(m-1)+m)(2^n-1)  (SURVEY.md 8d).  `e2e` = the same metric through
+zk_sumcheck_prove_host with HOST (pinned) tables: H2D of every table and D2H of the proof inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FIELD = 0  # BLS12-381 Fr
+SEED = 0x5EED000000000001
+
+
+def alg_muls(n, m, d):
+    return ((d + 1) * (m - 1) + m) * ((1 << n) - 1)
+
+
+def alg_bytes(n, m):
+    return 32 * m * ((1 << n) + 1.5 * ((1 << (n + 1)) - 2))
+
+
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for _, l in self.lines]
+        for l in rows:
+            p = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_run(n, m, d, steps, warmup):
+    """The reference's CPU algorithm (single-threaded, like the reference: no rayon/threads anywhere in it),
+    as the reference-shaped C port oracle/cpu_ref.c::zko_prove.  Returns (median s/step, list)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cref
+
+    tabs = [cref.gen_table(FIELD, SEED, k, n) for k in range(m)]
+    claim = cref.product_sum(FIELD, tabs, n)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        cref.prove(FIELD, tabs, n, d, claim, False, fast=False)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    m, d = args.m, args.degree
+    n_full = args.log_n if args.log_n else 26 + (args.gpus.bit_length() - 1)
+    n = args.cpu_log_n
+    times = cpu_reference_run(n, m, d, args.steps, min(args.warmup, 1))
+    sec = sum(times) / len(times)
+    value = alg_muls(n, m, d) / sec
+    sample = f"2^{n}-entry sample of the 2^{n_full}-entry workload (cost is linear in 2^n), {len(times)} timed proofs"
+    line = {
+        "impl": "reference", "metric": "sumcheck_prove_field_mul_per_s", "value": value, "unit": "field-mul/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u256 (4x64-bit Montgomery limbs)",
+        "data": "synthetic", "config": workload_config(n_full, m, d, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "field-mul/s", "cores": 1, "kind": "port", "sample": sample,
+                         "note": "reference-shaped C restatement (oracle/cpu_ref.c); the Rust reference cannot be built here and is single-threaded"},
+        "e2e": {"value": value, "unit": "field-mul/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "prove_ms_extrapolated_full": sec * 1e3 * (1 << (n_full - n)),
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(n, m, d, gpus):
+    return {"workload": f"BASELINE config 3 shape: degree-{d} product sumcheck prove_partial, {m} MLE tables x 2^{n} entries, BLS12-381 Fr"
+                        + (" (config 4 sharding)" if gpus > 1 else ""),
+            "log_n": n, "n_factors": m, "max_var_degree": d, "field": "bls12_381_fr", "table_bytes_total": 32 * m * (1 << n),
+            "sharding": f"strided by last-bound variables over {gpus} GPU(s)", "l2": "inputs larger than L2 (no flush needed)"}
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    import zk_b200 as zk
+    from zk_b200 import _ffi
+
+    lib = _ffi.lib()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    nccl_id = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(zk.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+    ctx = zk.Context(local_rank, rank=rank, world=world, nccl_id=nccl_id)
+    m, d = args.m, args.degree
+    n = args.log_n if args.log_n else 26 + (world.bit_length() - 1)
+    np1 = d + 1
+    ext = torch.cuda.ExternalStream(ctx.stream_ptr())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    def gen_tables():
+        return [zk.MultiLinearPolynomial.generate(n, k, seed=SEED, ctx=ctx) for k in range(m)]
+
+    rp = np.zeros((n, np1, 4), dtype=np.uint64)
+    ch = np.zeros((n, 4), dtype=np.uint64)
+    fin = np.zeros((m, 4), dtype=np.uint64)
+
+    # the claim (an input of the reference's prove(poly, sum)) — computed once, outside the timed region
+    tabs = gen_tables()
+    claim = zk.ProductPoly(tabs).sum_mont()
+    del tabs
+
+    def prove_resident(tabs):
+        arr = zk._table_array(tabs)
+        ctx.check(lib.zk_sumcheck_prove(ctx.h, arr, m, d, claim.ctypes.data, 0, rp.ctypes.data, ch.ctypes.data, fin.ctypes.data))
+
+    # ---- device-resident metric ------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    step_ms, fused_ms, launches0 = [], [], None
+    wall_t0 = wall_t1 = None
+    for it in range(args.warmup + args.steps):
+        tabs = gen_tables()  # untimed: prove consumes its tables
+        timed = it >= args.warmup
+        if timed and launches0 is None:
+            sampler.start()
+            time.sleep(0.25)
+            launches0 = ctx.launch_count()
+            wall_t0 = time.time()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        prove_resident(tabs)
+        e1.record(ext)
+        barrier()
+        if timed:
+            step_ms.append(e0.elapsed_time(e1))
+            r = ctx.last_round_ms()
+            fused_ms.append(r[1] if len(r) > 1 else r[0])
+        del tabs
+    wall_t1 = time.time()
+    launches = ctx.launch_count() - launches0 - args.steps * m  # minus the (untimed) generator launches
+    clocks = sampler.stop(wall_t0, wall_t1)
+    proof_digest = zk.keccak256(rp.tobytes() + ch.tobytes()).hex()
+
+    total_ms = sum(step_ms)
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = alg_muls(n, m, d) / (ms_per_step * 1e-3)
+
+    # ---- end-to-end metric: host (pinned) tables in, proof out, through zk_sumcheck_prove_host -----------------
+    e2e = None
+    if not args.no_e2e:
+        local_len = (1 << n) // world
+        host_bytes = 32 * local_len  # each rank stages ITS shard (entries rank, rank+world, ...) in pinned host memory
+        ptrs = []
+        for k in range(m):
+            p = C.c_void_p()
+            if lib.zk_host_alloc(host_bytes, C.byref(p)) != 0:
+                ptrs = None
+                break
+            ptrs.append(p)
+        if ptrs:
+            if True:
+                for k in range(m):
+                    t_loc = zk.MultiLinearPolynomial.generate(n, k, seed=SEED, ctx=ctx)
+                    ctx.check(lib.zk_table_download(ctx.h, t_loc._h, ptrs[k]))
+                    del t_loc
+                arr = (C.c_void_p * m)(*[p.value for p in ptrs])
+                e2e_ms = []
+                for it in range(min(args.warmup, 2) + args.steps):
+                    barrier()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(ext)
+                    ctx.check(lib.zk_sumcheck_prove_host(ctx.h, FIELD, arr, m, n, d, claim.ctypes.data, 0, rp.ctypes.data,
+                                                         ch.ctypes.data, fin.ctypes.data, None))
+                    e1.record(ext)
+                    barrier()
+                    if it >= min(args.warmup, 2):
+                        e2e_ms.append(e0.elapsed_time(e1))
+                assert zk.keccak256(rp.tobytes() + ch.tobytes()).hex() == proof_digest, "e2e proof differs from the resident proof"
+                tt = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device="cuda")
+                if dist is not None:
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                e2e_ms_step = float(tt.item()) / args.steps
+                e2e = {"value": alg_muls(n, m, d) / (e2e_ms_step * 1e-3), "unit": "field-mul/s", "ms_per_step": e2e_ms_step,
+                       "h2d_bytes_per_step": 32 * m * local_len * world + 32 * world, "d2h_bytes_per_step": world * (rp.nbytes + ch.nbytes + fin.nbytes),
+                       "api": "zk_sumcheck_prove_host (pinned host tables -> proof on host)"}
+                for p in ptrs:
+                    lib.zk_host_free(p)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel: the first fused fold+round-sum step (reads N, writes N/2 per factor) --------
+    peaks, peak_src = measured_peaks()
+    local_n0 = (1 << n) // world
+    fused_bytes = 48 * m * local_n0
+    fused_s = (sum(fused_ms) / len(fused_ms)) * 1e-3
+    achieved = fused_bytes / fused_s / 1e9
+    fused_muls = (2 * m + (d + 1) * (m - 1)) * (local_n0 // 4)
+    mb = ctx.microbench(FIELD)
+    roofline = {"bound": "hbm", "kernel": f"fold_round_poly_kernel<Fr381,{m},{d}> (first fused step)", "achieved": achieved,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_src,
+                "traffic": None, "algorithmic_bytes_per_launch": fused_bytes, "launch_ms": fused_s * 1e3,
+                "int_pipe": {"field_mul_per_s": fused_muls / fused_s, "standalone_fe_mul_per_s_peak": mb["fe_mul_per_s"],
+                             "frac_of_standalone_mul_peak": fused_muls / fused_s / mb["fe_mul_per_s"],
+                             "imad_wide_per_s_peak": mb["imad_wide_per_s"]},
+                "whole_prove": {"alg_bytes": alg_bytes(n, m) / world, "gbs": alg_bytes(n, m) / world / (ms_per_step * 1e-3) / 1e9}}
+
+    # ---- CPU baseline beside it (bounded sample, rank 0, N = 1 only) ----------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        ncpu = args.cpu_log_n
+        times = cpu_reference_run(ncpu, m, d, 1, 0)
+        cpu = {"value": alg_muls(ncpu, m, d) / times[0], "unit": "field-mul/s", "cores": 1, "kind": "port",
+               "sample": f"one reference-shaped proof at 2^{ncpu} entries ({times[0]:.1f} s); cost is linear in 2^n",
+               "host_cores_available": os.cpu_count()}
+
+    line = {
+        "metric": "sumcheck_prove_field_mul_per_s", "value": value, "unit": "field-mul/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs, IMAD.WIDE)", "data": "synthetic",
+        "config": workload_config(n, m, d, world), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu, "prove_ms": ms_per_step, "proof_keccak": proof_digest,
+        "round_kernel_ms": [round(x, 4) for x in ctx.last_round_ms()], "microbench": mb,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=0, help="total table size 2^n (default 26 + log2(gpus))")
+    ap.add_argument("--m", type=int, default=3)
+    ap.add_argument("--degree", type=int, default=3)
+    ap.add_argument("--cpu-log-n", type=int, default=22, help="size of the bounded CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

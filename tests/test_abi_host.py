@@ -1,0 +1,157 @@
+"""CPU suite, part 2: the C-ABI library loads and exports every symbol include/zk_b200.h declares, its
+host-side pieces (Keccak transcript, field conversions, verify_partial) agree with the oracle, and the
+data path refuses to run without a CUDA device (no CPU fallback).  No GPU compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import zkoracle as O
+from conftest import ROOT, hx
+
+
+def test_header_symbols_all_exported(zk):
+    hdr = open(os.path.join(ROOT, "include", "zk_b200.h")).read()
+    declared = set(re.findall(r"ZK_API[^;]*?\b(zk_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 50
+    from zk_b200 import _ffi
+
+    lib = _ffi.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in zk_b200.h but not exported"
+    assert declared == set(_ffi.SIGNATURES), declared ^ set(_ffi.SIGNATURES)
+
+
+def test_status_strings_are_reference_messages(zk):
+    from zk_b200 import _ffi
+
+    s = lambda i: _ffi.lib().zk_status_string(i).decode()
+    assert s(1) == "evaluation vec len should equal 2^n_vars"  # evaluation_form.rs:20
+    assert s(2) == "evaluate must assign to all variables"  # evaluation_form.rs:85
+    assert s(3) == "cannot create product polynomial from empty polynomials"  # product_poly.rs:16
+    assert s(4) == "cannot create product polynomial from polynomial that don't share the same number of variables"
+    assert s(5) == "invalid proof: require 1 round poly for each variable in poly"  # verifier.rs:18
+    assert s(6) == "couldn't evaluate initial poly"
+    assert s(7) == "verifier check failed: claimed_sum != p(0) + p(1)"
+    assert s(9) == "values must be a power of 2"  # fft/src/lib.rs:29
+
+
+def test_no_cpu_fallback_without_gpu(zk):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(zk.ZkError) as ei:
+        zk.Context(0)
+    assert ei.value.status == 14  # ZK_ERR_CUDA
+    # the product must not import the oracle
+    import sys
+
+    for mod in list(sys.modules):
+        if mod.startswith("zk_b200"):
+            src = getattr(sys.modules[mod], "__file__", "") or ""
+            if src.endswith(".py"):
+                text = open(src).read()
+                assert "zkoracle" not in text and "cref" not in text and "libzkoracle" not in text
+
+
+def test_product_sources_do_not_reference_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "zk_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle/" not in text and "zkoracle" not in text and "libzkoracle" not in text, f
+
+
+def test_keccak_and_transcript(zk, golden):
+    g = golden["transcript"]
+    assert zk.keccak256(b"").hex() == g["keccak_empty"]
+    assert zk.keccak256(b"abc").hex() == g["keccak_abc"]
+    assert zk.keccak256(b"a" * 200).hex() == g["keccak_200x61"]
+    assert zk.keccak256(bytes(136)).hex() == g["keccak_136x00"]
+    for n in (0, 1, 135, 136, 137, 271, 272, 273, 1000):
+        data = bytes((i * 7 + n) & 0xFF for i in range(n))
+        assert zk.keccak256(data) == O.keccak256(data)
+    tr = zk.Transcript()
+    tr.append(b"zk-b200 transcript golden")
+    tr.append(bytes(range(200)))
+    got = [hex(tr.sample_field_element(zk.BLS12_381_FR)) for _ in range(3)]
+    tr.append(b"more")
+    got.append(hex(tr.sample_field_element(zk.BLS12_377_FR)))
+    assert got == g["challenges"]
+    tr2 = zk.Transcript()
+    tr2.append(b"x")
+    ot = O.Transcript()
+    ot.append(b"x")
+    assert tr2.sample_n_field_elements(4) == ot.sample_n_field_elements(O.BLS12_381_FR, 4)
+
+
+@pytest.mark.parametrize("fid", [0, 1])
+def test_field_helpers_vs_oracle(zk, cref, fid):
+    from zk_b200 import _ffi
+
+    lib = _ffi.lib()
+    FF = O.FIELDS[fid]
+    rng = np.random.default_rng(5 + fid)
+    vals = [int.from_bytes(rng.bytes(32), "little") % FF.p for _ in range(64)] + [0, 1, FF.p - 1, 2, FF.p - 2]
+    mont = zk.to_mont(fid, vals)
+    assert (mont == cref.ints_to_mont(fid, vals)).all()
+    assert zk.from_mont(fid, mont) == vals
+    # values >= p are reduced like Fr::from / from_be_bytes_mod_order
+    assert zk.from_mont(fid, zk.to_mont(fid, [FF.p, FF.p + 5, 2**256 - 1])) == [0, 5, (2**256 - 1) % FF.p]
+    out = np.zeros(4, dtype=np.uint64)
+    for a, b in zip(vals[:-1], vals[1:]):
+        am, bm = zk.to_mont(fid, [a])[0], zk.to_mont(fid, [b])[0]
+        lib.zk_field_mul(fid, am.ctypes.data, bm.ctypes.data, out.ctypes.data)
+        assert zk.from_mont(fid, out)[0] == a * b % FF.p
+        lib.zk_field_add(fid, am.ctypes.data, bm.ctypes.data, out.ctypes.data)
+        assert zk.from_mont(fid, out)[0] == (a + b) % FF.p
+        lib.zk_field_sub(fid, am.ctypes.data, bm.ctypes.data, out.ctypes.data)
+        assert zk.from_mont(fid, out)[0] == (a - b) % FF.p
+        if a:
+            assert lib.zk_field_inverse(fid, am.ctypes.data, out.ctypes.data) == 0
+            assert zk.from_mont(fid, out)[0] == pow(a, -1, FF.p)
+    zero = zk.to_mont(fid, [0])[0]
+    assert lib.zk_field_inverse(fid, zero.ctypes.data, out.ctypes.data) == 12
+    be = np.zeros(32 * len(vals), dtype=np.uint8)
+    lib.zk_field_to_bytes_be(fid, mont.ctypes.data, len(vals), be.ctypes.data)
+    assert be.tobytes() == b"".join(FF.to_bytes_be(v) for v in vals)
+    raw = bytes(range(224, 256))
+    lib.zk_field_from_be_bytes_mod_order(fid, raw, out.ctypes.data)
+    assert zk.from_mont(fid, out)[0] == int.from_bytes(raw, "big") % FF.p
+    lib.zk_field_from_u64(fid, 2**64 - 1, out.ctypes.data)
+    assert zk.from_mont(fid, out)[0] == 2**64 - 1
+    for n in (1, 2, 4, 1 << 20, 1 << FF.two_adicity):
+        assert lib.zk_field_root_of_unity(fid, n, out.ctypes.data) == 0
+        assert zk.from_mont(fid, out)[0] == FF.get_root_of_unity(n)
+    assert lib.zk_field_root_of_unity(fid, 1 << (FF.two_adicity + 1), out.ctypes.data) == 10
+    assert lib.zk_field_root_of_unity(fid, 3, out.ctypes.data) == 10
+
+
+def test_verify_partial_host_vs_golden(zk, golden):
+    """SumcheckVerifier::verify_partial is host-only: run it on golden proofs (no GPU needed)."""
+    for c in golden["small_cases"] + golden["seeded_cases"]:
+        if c["absorb"]:
+            continue
+        proof = zk.SumcheckProof.from_values(c["field"], hx(c["claim"]), [[hx(x) for x in r] for r in c["round_polys"]])
+        if c["degree"] < c.get("m", 1):
+            # MAX_VAR_DEGREE below the true degree is not validated by the prover (prover.rs:48-56); the
+            # verifier's interpolation is then wrong and it must reject exactly like the reference would
+            with pytest.raises(zk.ZkError, match="claimed_sum != p\\(0\\) \\+ p\\(1\\)"):
+                zk.SumcheckVerifier.verify_partial(proof)
+            with pytest.raises(O.OracleError):
+                O.SumcheckVerifier.verify_partial(O.FIELDS[c["field"]], O.SumcheckProof(hx(c["claim"]), [[hx(x) for x in r] for r in c["round_polys"]]))
+            continue
+        sub = zk.SumcheckVerifier.verify_partial(proof)
+        assert [hex(x) for x in sub.challenges] == c["challenges"], c["name"]
+        prod = 1
+        for x in c["finals"]:
+            prod = prod * hx(x) % O.FIELDS[c["field"]].p
+        assert sub.sum == prod
+    # wrong claim -> the reference's Err string
+    c = {x["name"]: x for x in golden["small_cases"]}["B2_prove_partial_2ab3bc_sum10"]
+    bad = zk.SumcheckProof.from_values(0, 12, [[hx(x) for x in r] for r in c["round_polys"]])
+    with pytest.raises(zk.ZkError, match="claimed_sum != p\\(0\\) \\+ p\\(1\\)"):
+        zk.SumcheckVerifier.verify_partial(bad)

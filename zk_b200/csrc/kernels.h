@@ -1,0 +1,95 @@
+// kernels.h — internal launch interface between the C-ABI host layer (api.cpp) and the sm_100a
+// kernels (kernels_*.cu).  Not part of the public boundary; see include/zk_b200.h for that.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "field.cuh"
+
+namespace zk {
+
+constexpr int kMaxFactors = 8;   // ProductPoly factor count supported on the device
+constexpr int kMaxDegree = 15;   // MAX_VAR_DEGREE supported (round polynomial has kMaxDegree+1 evaluations)
+constexpr int kMaxGridBlocks = 148 * 16;
+
+struct TablePtrs {
+    Fe* t[kMaxFactors];
+};
+
+// Per-context scratch used by the reducing kernels.
+struct ReduceScratch {
+    Fe* block_partials;      // [kMaxGridBlocks * (kMaxDegree+1)] device
+    unsigned* ticket;        // device, zero between launches
+    Fe* result_dev;          // [(kMaxDegree+1)] device copy of the last result
+    Fe* result_host;         // [(kMaxDegree+1)] pinned+mapped host memory (device-visible alias below)
+    Fe* result_host_devptr;  // device pointer aliasing result_host
+    int num_sms;
+};
+
+// ---- sumcheck hot path (kernels_sumcheck.cu) ---------------------------------------------------
+// Round polynomial evaluations S(t) = sum_{j<half} prod_k [A_k[j] + t (A_k[j+half] - A_k[j])], t = 0..degree.
+// (sumcheck/src/prover.rs:49-56).  Result (degree+1 elements, Montgomery, reduced) lands in
+// scratch.result_dev and scratch.result_host.
+cudaError_t launch_round_poly(int field, const TablePtrs& tabs, int m, int degree, uint64_t half,
+                              const ReduceScratch& scratch, cudaStream_t stream, int* launches);
+// In-place fold of every factor at r (prover.rs:64 -> evaluation_form.rs:40-80 with initial_var = 0):
+// T[j] = T[j] - r (T[j] - T[j+half]), j < half.
+cudaError_t launch_fold(int field, const TablePtrs& tabs, int m, uint64_t half, const Fe& r, cudaStream_t stream,
+                        int* launches);
+// Fused: fold the n_prev-entry tables at r (halving them in place), and in the same pass produce the
+// next round's polynomial over the folded tables.  n_prev >= 4.
+cudaError_t launch_fold_round_poly(int field, const TablePtrs& tabs, int m, int degree, uint64_t n_prev, const Fe& r,
+                                   const ReduceScratch& scratch, cudaStream_t stream, int* launches);
+// sum_j prod_k A_k[j]  (the claim): result in scratch.result_dev[0] / result_host[0].
+cudaError_t launch_product_sum(int field, const TablePtrs& tabs, int m, uint64_t n, const ReduceScratch& scratch,
+                               cudaStream_t stream, int* launches);
+// true if (m, degree) has a fully fused template instantiation
+bool has_fused_path(int m, int degree);
+
+// ---- MLE utilities (kernels_mle.cu) --------------------------------------------------------------
+// General partial_evaluate step for variable `initial_var` of an nv-variable table: out[k] = fold of the
+// pair (insert_bit(k,pos,0), |1<<pos), pos = nv-1-initial_var; out-of-place (evaluation_form.rs:54-72).
+cudaError_t launch_fold_var(int field, const Fe* in, Fe* out, unsigned nv, unsigned initial_var, const Fe& a,
+                            cudaStream_t stream, int* launches);
+// out[j] = prod_k A_k[j]  (product_poly.rs:66-74)
+cudaError_t launch_prod_reduce(int field, const TablePtrs& tabs, int m, uint64_t n, Fe* out, cudaStream_t stream,
+                               int* launches);
+// Montgomery -> 32-byte big-endian canonical (evaluation_form.rs:97-103)
+cudaError_t launch_to_bytes(int field, const Fe* in, uint64_t n, uint8_t* out, cudaStream_t stream, int* launches);
+// Montgomery <-> canonical little-endian limbs, in place
+cudaError_t launch_convert(int field, Fe* data, uint64_t n, bool to_mont, cudaStream_t stream, int* launches);
+// Synthetic table: entry j of the local shard is global index first + j*stride (SURVEY.md 8d generator)
+cudaError_t launch_generate(int field, Fe* out, uint64_t count, uint64_t seed, uint64_t table_id, uint64_t first,
+                            uint64_t stride, cudaStream_t stream, int* launches);
+// out[j*G + q] = in[q*L + j]: re-interleave the all-gathered residual shards (q-major) into global order
+cudaError_t launch_interleave(const Fe* in, Fe* out, uint64_t local_len, unsigned world, cudaStream_t stream,
+                              int* launches);
+// Widen (D+1) elements into u64 lanes (one 32-bit limb per lane) for an exact ncclSum all-reduce, and the
+// inverse: carry-propagate the lane sums and reduce mod p.
+cudaError_t launch_widen(const Fe* in, uint64_t* lanes, int count, cudaStream_t stream, int* launches);
+cudaError_t launch_narrow(int field, const uint64_t* lanes, Fe* out_dev, Fe* out_host_devptr, int count,
+                          cudaStream_t stream, int* launches);
+
+// ---- NTT (kernels_ntt.cu) --------------------------------------------------------------------
+struct NttPlan;
+cudaError_t ntt_plan_create(int field, unsigned log_n, bool inverse, cudaStream_t stream, NttPlan** out, int* launches);
+void ntt_plan_destroy(NttPlan*);
+// natural order in -> natural order out, in place on `data` (uses plan-owned scratch)
+cudaError_t ntt_execute(NttPlan* plan, Fe* data, cudaStream_t stream, int* launches);
+
+// ---- micro-benchmarks (microbench.cu) ------------------------------------------------------------
+struct MicrobenchResult {
+    double imad_wide_per_s;     // independent IMAD.WIDE.U32 per second, whole chip
+    double imad_lo_per_s;       // IMAD (32-bit lo) per second
+    double iadd3_per_s;         // IADD3 per second
+    double mixed_per_s;         // IMAD.WIDE + IADD3 interleaved: instructions per second
+    double fe_mul_per_s;        // standalone Montgomery multiplications per second (the field-mul ceiling)
+    double copy_gbs;            // 256-bit streaming copy GB/s (read+write)
+    double read_gbs;            // 256-bit streaming read GB/s
+    double sm_clock_mhz;        // clock64-derived SM clock during the IMAD run
+};
+cudaError_t run_microbench(int field, MicrobenchResult* out, cudaStream_t stream);
+
+}  // namespace zk

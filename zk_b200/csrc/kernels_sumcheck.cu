@@ -1,0 +1,356 @@
+// kernels_sumcheck.cu — the sumcheck prover hot path on sm_100a.
+//
+// What it replaces in the reference (paths relative to /root/reference):
+//   sumcheck/src/prover.rs:49-56   for t in 0..=D: poly.partial_evaluate(0,[t]).prod_reduce().iter().sum()
+//   sumcheck/src/prover.rs:64      poly = poly.partial_evaluate(0,[challenge])
+//   polynomial/src/multilinear/evaluation_form.rs:40-80 (pair (j, j+N/2), left - a*(left-right))
+//   polynomial/src/product_poly.rs:66-74 (element-wise product)
+// The reference materialises (D+2)*m table clones, D+1 product vectors and D+1 sum passes per round;
+// here one pass per round streams every factor table exactly once:
+//   round 0            : round_poly_kernel      reads N            (sum only)
+//   round i >= 1       : fold_round_poly_kernel reads N_{i-1}, writes N_{i-1}/2   (fold at r_{i-1} fused
+//                        with the sums of round i: thread j owns T[j], T[j+q], T[j+2q], T[j+3q], q = N_{i-1}/4,
+//                        writes the two folded values back to T[j], T[j+q] — in place and race-free)
+//   after the last rnd : fold_kernel            2 -> 1
+// Integer modular sums are order independent, so any reduction tree is bit-exact with the reference's
+// sequential `.sum()`.  Reduction: registers -> warp shuffle -> shared memory -> per-block partials in
+// global memory -> the last block to finish (atomic ticket) folds the partials and publishes the
+// D+1 evaluations to device memory and to mapped pinned host memory.
+#include "kernels.h"
+
+namespace zk {
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kWarps = kThreads / 32;
+
+__device__ __forceinline__ Fe ld_fe_cg(const Fe* p) {  // L2-coherent load (other blocks' partials)
+    Fe r;
+    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
+                   "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+
+template <class F>
+__device__ __forceinline__ Fe warp_sum(Fe v, int width = 32) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        if (off < width) {
+            Fe o;
+#pragma unroll
+            for (int i = 0; i < 8; i++) o.v[i] = __shfl_xor_sync(0xffffffffu, v.v[i], off);
+            v = fe_add<F>(v, o);
+        }
+    }
+    return v;
+}
+
+struct ReduceArgs {
+    Fe* block_partials;
+    unsigned* ticket;
+    Fe* result_dev;
+    Fe* result_host;
+    int out_slot;
+};
+
+// Block-level reduction of NP per-thread accumulators, then grid-level via last-block-done.
+template <class F, int NP>
+__device__ __forceinline__ void reduce_publish(Fe* acc, const ReduceArgs& ra) {
+    __shared__ Fe sh[NP][kWarps];
+    __shared__ unsigned s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int t = 0; t < NP; t++) {
+        Fe v = warp_sum<F>(acc[t]);
+        if (lane == 0) sh[t][warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll 1
+        for (int t = 0; t < NP; t++) {
+            Fe v = (lane < kWarps) ? sh[t][lane] : fe_zero<F>();
+            v = warp_sum<F>(v, kWarps);
+            if (lane == 0) st_fe(ra.block_partials + (size_t)blockIdx.x * NP + t, v);
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned tk = atomicAdd(ra.ticket, 1u);
+        s_last = (tk == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+#pragma unroll 1
+    for (int t = 0; t < NP; t++) {
+        Fe v = fe_zero<F>();
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += kThreads)
+            v = fe_add<F>(v, ld_fe_cg(ra.block_partials + (size_t)b * NP + t));
+        v = warp_sum<F>(v);
+        __syncthreads();  // sh reuse across t
+        if (lane == 0) sh[0][warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            Fe w = (lane < kWarps) ? sh[0][lane] : fe_zero<F>();
+            w = warp_sum<F>(w, kWarps);
+            if (lane == 0) {
+                st_fe(ra.result_dev + ra.out_slot + t, w);
+                st_fe(ra.result_host + ra.out_slot + t, w);
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        *ra.ticket = 0;  // ready for the next launch on this stream
+        __threadfence_system();
+    }
+}
+
+// acc[t] += prod_k e_k(t) for t = 0..D where e_k(0)=lo_k, e_k(1)=hi_k, e_k(t+1)=e_k(t)+(hi_k-lo_k).
+// lo/hi are clobbered.
+template <class F, int M, int D>
+__device__ __forceinline__ void accumulate_products(Fe* lo, Fe* hi, Fe* acc) {
+    {
+        Fe pr = lo[0];
+#pragma unroll
+        for (int k = 1; k < M; k++) pr = fe_mul<F>(pr, lo[k]);
+        acc[0] = fe_add<F>(acc[0], pr);
+    }
+    if (D >= 1) {
+        Fe pr = hi[0];
+#pragma unroll
+        for (int k = 1; k < M; k++) pr = fe_mul<F>(pr, hi[k]);
+        acc[1] = fe_add<F>(acc[1], pr);
+    }
+    if (D >= 2) {
+#pragma unroll
+        for (int k = 0; k < M; k++) lo[k] = fe_sub<F>(hi[k], lo[k]);  // lo := d
+#pragma unroll
+        for (int t = 2; t <= D; t++) {
+#pragma unroll
+            for (int k = 0; k < M; k++) hi[k] = fe_add<F>(hi[k], lo[k]);
+            Fe pr = hi[0];
+#pragma unroll
+            for (int k = 1; k < M; k++) pr = fe_mul<F>(pr, hi[k]);
+            acc[t] = fe_add<F>(acc[t], pr);
+        }
+    }
+}
+
+template <class F, int M, int D>
+__global__ void __launch_bounds__(kThreads) round_poly_kernel(TablePtrs tabs, uint64_t half, ReduceArgs ra) {
+    Fe acc[D + 1];
+#pragma unroll
+    for (int t = 0; t <= D; t++) acc[t] = fe_zero<F>();
+    const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+#pragma unroll 1
+    for (uint64_t j = (uint64_t)blockIdx.x * kThreads + threadIdx.x; j < half; j += stride) {
+        Fe lo[M], hi[M];
+#pragma unroll
+        for (int k = 0; k < M; k++) {
+            lo[k] = ld_fe_stream(tabs.t[k] + j);
+            hi[k] = ld_fe_stream(tabs.t[k] + j + half);
+        }
+        accumulate_products<F, M, D>(lo, hi, acc);
+    }
+    reduce_publish<F, D + 1>(acc, ra);
+}
+
+template <class F, int M, int D>
+__global__ void __launch_bounds__(kThreads)
+    fold_round_poly_kernel(TablePtrs tabs, uint64_t q, Fe r, ReduceArgs ra) {
+    Fe acc[D + 1];
+#pragma unroll
+    for (int t = 0; t <= D; t++) acc[t] = fe_zero<F>();
+    const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+#pragma unroll 1
+    for (uint64_t j = (uint64_t)blockIdx.x * kThreads + threadIdx.x; j < q; j += stride) {
+        Fe lo[M], hi[M];
+#pragma unroll
+        for (int k = 0; k < M; k++) {
+            Fe* T = tabs.t[k];
+            Fe x0 = ld_fe_stream(T + j), x2 = ld_fe_stream(T + j + 2 * q);
+            lo[k] = fe_fold<F>(x0, x2, r);
+            st_fe(T + j, lo[k]);
+            Fe x1 = ld_fe_stream(T + j + q), x3 = ld_fe_stream(T + j + 3 * q);
+            hi[k] = fe_fold<F>(x1, x3, r);
+            st_fe(T + j + q, hi[k]);
+        }
+        accumulate_products<F, M, D>(lo, hi, acc);
+    }
+    reduce_publish<F, D + 1>(acc, ra);
+}
+
+// grid.y = factor index
+template <class F>
+__global__ void __launch_bounds__(256) fold_kernel(TablePtrs tabs, uint64_t half, Fe r) {
+    Fe* T = tabs.t[blockIdx.y];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < half; j += stride) {
+        Fe l = ld_fe_stream(T + j), h = ld_fe_stream(T + j + half);
+        st_fe(T + j, fe_fold<F>(l, h, r));
+    }
+}
+
+// Generic (any m <= kMaxFactors): one evaluation point per launch,
+// sum_j prod_k [lo_k - t (lo_k - hi_k)]   (t given in Montgomery form; is_zero/is_one shortcuts are
+// the same field function, evaluation_form.rs:61-62).
+template <class F>
+__global__ void __launch_bounds__(kThreads) eval_at_kernel(TablePtrs tabs, int m, uint64_t half, Fe t, ReduceArgs ra) {
+    Fe acc[1];
+    acc[0] = fe_zero<F>();
+    const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+#pragma unroll 1
+    for (uint64_t j = (uint64_t)blockIdx.x * kThreads + threadIdx.x; j < half; j += stride) {
+        Fe pr = fe_fold<F>(ld_fe_stream(tabs.t[0] + j), ld_fe_stream(tabs.t[0] + j + half), t);
+#pragma unroll 1
+        for (int k = 1; k < m; k++)
+            pr = fe_mul<F>(pr, fe_fold<F>(ld_fe_stream(tabs.t[k] + j), ld_fe_stream(tabs.t[k] + j + half), t));
+        acc[0] = fe_add<F>(acc[0], pr);
+    }
+    reduce_publish<F, 1>(acc, ra);
+}
+
+template <class F>
+__global__ void __launch_bounds__(kThreads) product_sum_kernel(TablePtrs tabs, int m, uint64_t n, ReduceArgs ra) {
+    Fe acc[1];
+    acc[0] = fe_zero<F>();
+    const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+#pragma unroll 1
+    for (uint64_t j = (uint64_t)blockIdx.x * kThreads + threadIdx.x; j < n; j += stride) {
+        Fe pr = ld_fe_stream(tabs.t[0] + j);
+#pragma unroll 1
+        for (int k = 1; k < m; k++) pr = fe_mul<F>(pr, ld_fe_stream(tabs.t[k] + j));
+        acc[0] = fe_add<F>(acc[0], pr);
+    }
+    reduce_publish<F, 1>(acc, ra);
+}
+
+// ---- launch helpers ----------------------------------------------------------------------------
+template <class K>
+int blocks_per_sm(K kernel, int threads) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1) n = 1;
+    return n;
+}
+inline unsigned grid_for(uint64_t items, int threads, int num_sms, int bpsm) {
+    uint64_t need = (items + threads - 1) / threads;
+    uint64_t cap = (uint64_t)num_sms * bpsm;
+    if (cap > (uint64_t)kMaxGridBlocks) cap = kMaxGridBlocks;
+    if (need < 1) need = 1;
+    return (unsigned)(need < cap ? need : cap);
+}
+inline ReduceArgs make_ra(const ReduceScratch& s, int slot) {
+    return ReduceArgs{s.block_partials, s.ticket, s.result_dev, s.result_host_devptr, slot};
+}
+template <class F>
+Fe small_constant(unsigned t);  // Montgomery form of small integer t (host side)
+
+template <class F, int M, int D>
+cudaError_t do_round_poly(const TablePtrs& tabs, uint64_t half, const ReduceScratch& s, cudaStream_t st) {
+    static int bpsm = blocks_per_sm(round_poly_kernel<F, M, D>, kThreads);
+    unsigned grid = grid_for(half, kThreads, s.num_sms, bpsm);
+    round_poly_kernel<F, M, D><<<grid, kThreads, 0, st>>>(tabs, half, make_ra(s, 0));
+    return cudaGetLastError();
+}
+template <class F, int M, int D>
+cudaError_t do_fold_round_poly(const TablePtrs& tabs, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st) {
+    static int bpsm = blocks_per_sm(fold_round_poly_kernel<F, M, D>, kThreads);
+    unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
+    fold_round_poly_kernel<F, M, D><<<grid, kThreads, 0, st>>>(tabs, q, r, make_ra(s, 0));
+    return cudaGetLastError();
+}
+
+// host-side Montgomery form of a small integer: t * R mod p by repeated addition of R (t <= kMaxDegree)
+template <class F>
+Fe host_small_mont(unsigned t) {
+    // 8x32 limb add/sub on the host
+    uint32_t acc[8] = {0};
+    for (unsigned it = 0; it < t; it++) {
+        uint64_t c = 0;
+        for (int i = 0; i < 8; i++) { c += (uint64_t)acc[i] + F::one(i); acc[i] = (uint32_t)c; c >>= 32; }
+        // conditional subtract p
+        uint32_t tmp[8]; int64_t b = 0;
+        for (int i = 0; i < 8; i++) { int64_t d = (int64_t)acc[i] - F::p(i) + b; tmp[i] = (uint32_t)d; b = d >> 32; }
+        if (c || b == 0) for (int i = 0; i < 8; i++) acc[i] = tmp[i];
+    }
+    Fe r;
+    for (int i = 0; i < 8; i++) r.v[i] = acc[i];
+    return r;
+}
+
+template <class F>
+cudaError_t round_poly_dispatch(const TablePtrs& tabs, int m, int degree, uint64_t half, const ReduceScratch& s,
+                                cudaStream_t st, int* launches) {
+    if (m == 1 && degree == 1) { ++*launches; return do_round_poly<F, 1, 1>(tabs, half, s, st); }
+    if (m == 2 && degree == 2) { ++*launches; return do_round_poly<F, 2, 2>(tabs, half, s, st); }
+    if (m == 3 && degree == 3) { ++*launches; return do_round_poly<F, 3, 3>(tabs, half, s, st); }
+    static int bpsm = blocks_per_sm(eval_at_kernel<F>, kThreads);
+    unsigned grid = grid_for(half, kThreads, s.num_sms, bpsm);
+    for (int t = 0; t <= degree; t++) {
+        eval_at_kernel<F><<<grid, kThreads, 0, st>>>(tabs, m, half, host_small_mont<F>((unsigned)t), make_ra(s, t));
+        ++*launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+template <class F>
+cudaError_t fold_dispatch(const TablePtrs& tabs, int m, uint64_t half, const Fe& r, const ReduceScratch* s,
+                          cudaStream_t st, int* launches) {
+    int num_sms = s ? s->num_sms : 148;
+    uint64_t need = (half + 255) / 256;
+    uint64_t cap = (uint64_t)num_sms * 8;
+    dim3 grid((unsigned)(need < cap ? (need ? need : 1) : cap), (unsigned)m);
+    fold_kernel<F><<<grid, 256, 0, st>>>(tabs, half, r);
+    ++*launches;
+    return cudaGetLastError();
+}
+template <class F>
+cudaError_t fold_round_poly_dispatch(const TablePtrs& tabs, int m, int degree, uint64_t n_prev, const Fe& r,
+                                     const ReduceScratch& s, cudaStream_t st, int* launches) {
+    const uint64_t q = n_prev / 4;
+    if (m == 1 && degree == 1) { ++*launches; return do_fold_round_poly<F, 1, 1>(tabs, q, r, s, st); }
+    if (m == 2 && degree == 2) { ++*launches; return do_fold_round_poly<F, 2, 2>(tabs, q, r, s, st); }
+    if (m == 3 && degree == 3) { ++*launches; return do_fold_round_poly<F, 3, 3>(tabs, q, r, s, st); }
+    cudaError_t e = fold_dispatch<F>(tabs, m, n_prev / 2, r, &s, st, launches);
+    if (e != cudaSuccess) return e;
+    return round_poly_dispatch<F>(tabs, m, degree, n_prev / 4, s, st, launches);
+}
+template <class F>
+cudaError_t product_sum_dispatch(const TablePtrs& tabs, int m, uint64_t n, const ReduceScratch& s, cudaStream_t st,
+                                 int* launches) {
+    static int bpsm = blocks_per_sm(product_sum_kernel<F>, kThreads);
+    unsigned grid = grid_for(n, kThreads, s.num_sms, bpsm);
+    product_sum_kernel<F><<<grid, kThreads, 0, st>>>(tabs, m, n, make_ra(s, 0));
+    ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool has_fused_path(int m, int degree) { return m == degree && m >= 1 && m <= 3; }
+
+cudaError_t launch_round_poly(int field, const TablePtrs& tabs, int m, int degree, uint64_t half,
+                              const ReduceScratch& scratch, cudaStream_t stream, int* launches) {
+    return field == Fr381::ID ? round_poly_dispatch<Fr381>(tabs, m, degree, half, scratch, stream, launches)
+                              : round_poly_dispatch<Fr377>(tabs, m, degree, half, scratch, stream, launches);
+}
+cudaError_t launch_fold(int field, const TablePtrs& tabs, int m, uint64_t half, const Fe& r, cudaStream_t stream,
+                        int* launches) {
+    return field == Fr381::ID ? fold_dispatch<Fr381>(tabs, m, half, r, nullptr, stream, launches)
+                              : fold_dispatch<Fr377>(tabs, m, half, r, nullptr, stream, launches);
+}
+cudaError_t launch_fold_round_poly(int field, const TablePtrs& tabs, int m, int degree, uint64_t n_prev, const Fe& r,
+                                   const ReduceScratch& scratch, cudaStream_t stream, int* launches) {
+    return field == Fr381::ID ? fold_round_poly_dispatch<Fr381>(tabs, m, degree, n_prev, r, scratch, stream, launches)
+                              : fold_round_poly_dispatch<Fr377>(tabs, m, degree, n_prev, r, scratch, stream, launches);
+}
+cudaError_t launch_product_sum(int field, const TablePtrs& tabs, int m, uint64_t n, const ReduceScratch& scratch,
+                               cudaStream_t stream, int* launches) {
+    return field == Fr381::ID ? product_sum_dispatch<Fr381>(tabs, m, n, scratch, stream, launches)
+                              : product_sum_dispatch<Fr377>(tabs, m, n, scratch, stream, launches);
+}
+
+}  // namespace zk
