@@ -244,7 +244,11 @@ __device__ __forceinline__ void mont_row(uint32_t* X, uint32_t* Y, const uint32_
         madc4_rshift(Y, X[0], a[1], a[3], a[5], a[7], b);
         cmad4(X, a[0], a[2], a[4], a[6], b, Y[7]);
     }
-    const uint32_t m = 0u - X[0];  // -p^-1 mod 2^32 == 0xffffffff for both moduli
+    // m = -X[0]: -p^-1 mod 2^32 == 0xffffffff for both moduli.  Kept opaque (asm volatile): if the
+    // optimizer sees the negation it folds it into the multiply-adds below and ptxas then emits split
+    // IMAD.X + IMAD.HI.U32.X pairs (2 FMA-pipe slots per product) instead of one IMAD.WIDE.U32.X.
+    uint32_t m;
+    asm volatile("sub.u32 %0, 0, %1;" : "=r"(m) : "r"(X[0]));
     // total value stays < 2^288 (a < p), so the Y chain never carries out of column 8
     cmad4_nocarry(Y, F::p(1), F::p(3), F::p(5), F::p(7), m);
     cmad4(X, F::p(0), F::p(2), F::p(4), F::p(6), m, Y[7]);

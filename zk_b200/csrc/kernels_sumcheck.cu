@@ -22,6 +22,9 @@ namespace zk {
 namespace {
 
 constexpr int kThreads = 128;
+#ifndef ZK_MINB
+#define ZK_MINB 1
+#endif
 constexpr int kWarps = kThreads / 32;
 
 __device__ __forceinline__ Fe ld_fe_cg(const Fe* p) {  // L2-coherent load (other blocks' partials)
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(kThreads) round_poly_kernel(TablePtrs tabs, ui
 }
 
 template <class F, int M, int D>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, ZK_MINB)
     fold_round_poly_kernel(TablePtrs tabs, uint64_t q, Fe r, ReduceArgs ra) {
     Fe acc[D + 1];
 #pragma unroll
