@@ -7,8 +7,8 @@
 //   polynomial/src/product_poly.rs:66-74 (element-wise product)
 // The reference materialises (D+2)*m table clones, D+1 product vectors and D+1 sum passes per round;
 // here one pass per round streams every factor table exactly once:
-//   round 0            : round_poly_kernel      reads N            (sum only)
-//   round i >= 1       : fold_round_poly_kernel reads N_{i-1}, writes N_{i-1}/2   (fold at r_{i-1} fused
+//   round 0            : round_kernel<FOLD=false> reads N            (sum only)
+//   round i >= 1       : round_kernel<FOLD=true>  reads N_{i-1}, writes N_{i-1}/2   (fold at r_{i-1} fused
 //                        with the sums of round i: thread j owns T[j], T[j+q], T[j+2q], T[j+3q], q = N_{i-1}/4,
 //                        writes the two folded values back to T[j], T[j+q] — in place and race-free)
 //   after the last rnd : fold_kernel            2 -> 1
@@ -22,9 +22,6 @@ namespace zk {
 namespace {
 
 constexpr int kThreads = 128;
-#ifndef ZK_MINB
-#define ZK_MINB 1
-#endif
 constexpr int kWarps = kThreads / 32;
 
 __device__ __forceinline__ Fe ld_fe_cg(const Fe* p) {  // L2-coherent load (other blocks' partials)
@@ -110,77 +107,68 @@ __device__ __forceinline__ void reduce_publish(Fe* acc, const ReduceArgs& ra) {
     }
 }
 
-// acc[t] += prod_k e_k(t) for t = 0..D where e_k(0)=lo_k, e_k(1)=hi_k, e_k(t+1)=e_k(t)+(hi_k-lo_k).
-// lo/hi are clobbered.
-template <class F, int M, int D>
-__device__ __forceinline__ void accumulate_products(Fe* lo, Fe* hi, Fe* acc) {
-    {
-        Fe pr = lo[0];
+// One hypercube item, all factors: lo_k / hi_k are the pair values of factor k for this item (after the
+// optional fold).  pr[t] = prod_k e_k(t), e_k(0) = lo_k, e_k(1) = hi_k, e_k(t+1) = e_k(t) + (hi_k - lo_k)
+// (prover.rs:49-56 evaluates at t = 0..D by a full partial_evaluate + prod_reduce each; the values are the
+// same field elements).  Factors are visited sequentially so that only the D+1 running products and one
+// factor's pair are live: registers stay low enough for 4-5 resident blocks per SM, which is what hides the
+// carry-chain latency of the multiplier, and the loop body (6 multiplications) stays inside the 32 KB
+// instruction cache.  `m` is a run-time value: one instantiation per degree serves every factor count.
+template <class F, int D, bool FOLD>
+__global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
+    round_kernel(TablePtrs tabs, int m, uint64_t q, Fe r_param, ReduceArgs ra) {
+    __shared__ Fe* s_tab[kMaxFactors];
+    if (threadIdx.x < kMaxFactors) s_tab[threadIdx.x] = tabs.t[threadIdx.x];
+    __syncthreads();
+    Fe r;  // the challenge, pinned into registers (a constant-bank multiplier operand defeats IMAD.WIDE fusion)
 #pragma unroll
-        for (int k = 1; k < M; k++) pr = fe_mul<F>(pr, lo[k]);
-        acc[0] = fe_add<F>(acc[0], pr);
-    }
-    if (D >= 1) {
-        Fe pr = hi[0];
-#pragma unroll
-        for (int k = 1; k < M; k++) pr = fe_mul<F>(pr, hi[k]);
-        acc[1] = fe_add<F>(acc[1], pr);
-    }
-    if (D >= 2) {
-#pragma unroll
-        for (int k = 0; k < M; k++) lo[k] = fe_sub<F>(hi[k], lo[k]);  // lo := d
-#pragma unroll
-        for (int t = 2; t <= D; t++) {
-#pragma unroll
-            for (int k = 0; k < M; k++) hi[k] = fe_add<F>(hi[k], lo[k]);
-            Fe pr = hi[0];
-#pragma unroll
-            for (int k = 1; k < M; k++) pr = fe_mul<F>(pr, hi[k]);
-            acc[t] = fe_add<F>(acc[t], pr);
-        }
-    }
-}
-
-template <class F, int M, int D>
-__global__ void __launch_bounds__(kThreads) round_poly_kernel(TablePtrs tabs, uint64_t half, ReduceArgs ra) {
-    Fe acc[D + 1];
-#pragma unroll
-    for (int t = 0; t <= D; t++) acc[t] = fe_zero<F>();
-    const uint64_t stride = (uint64_t)gridDim.x * kThreads;
-#pragma unroll 1
-    for (uint64_t j = (uint64_t)blockIdx.x * kThreads + threadIdx.x; j < half; j += stride) {
-        Fe lo[M], hi[M];
-#pragma unroll
-        for (int k = 0; k < M; k++) {
-            lo[k] = ld_fe_stream(tabs.t[k] + j);
-            hi[k] = ld_fe_stream(tabs.t[k] + j + half);
-        }
-        accumulate_products<F, M, D>(lo, hi, acc);
-    }
-    reduce_publish<F, D + 1>(acc, ra);
-}
-
-template <class F, int M, int D>
-__global__ void __launch_bounds__(kThreads, ZK_MINB)
-    fold_round_poly_kernel(TablePtrs tabs, uint64_t q, Fe r, ReduceArgs ra) {
+    for (int i = 0; i < 8; i++) asm volatile("mov.u32 %0, %1;" : "=r"(r.v[i]) : "r"(r_param.v[i]));
     Fe acc[D + 1];
 #pragma unroll
     for (int t = 0; t <= D; t++) acc[t] = fe_zero<F>();
     const uint64_t stride = (uint64_t)gridDim.x * kThreads;
 #pragma unroll 1
     for (uint64_t j = (uint64_t)blockIdx.x * kThreads + threadIdx.x; j < q; j += stride) {
-        Fe lo[M], hi[M];
+        Fe pr[D + 1];
+#pragma unroll 1
+        for (int k = 0; k < m; k++) {
+            Fe* T = s_tab[k];
+            Fe lo, hi;
+            if (FOLD) {  // T has 4q entries: fold (j, j+2q) and (j+q, j+3q) at r, write back to j and j+q
+                Fe x0 = ld_fe_stream(T + j), x2 = ld_fe_stream(T + j + 2 * q);
+                Fe x1 = ld_fe_stream(T + j + q), x3 = ld_fe_stream(T + j + 3 * q);
+                lo = fe_fold<F>(x0, x2, r);
+                st_fe(T + j, lo);
+                hi = fe_fold<F>(x1, x3, r);
+                st_fe(T + j + q, hi);
+            } else {  // T has 2q entries: the pair is (j, j+q)
+                lo = ld_fe_stream(T + j);
+                hi = ld_fe_stream(T + j + q);
+            }
+            if (k == 0) {
+                pr[0] = lo;
+                if (D >= 1) pr[1] = hi;
+                if (D >= 2) {
+                    Fe d = fe_sub<F>(hi, lo);
 #pragma unroll
-        for (int k = 0; k < M; k++) {
-            Fe* T = tabs.t[k];
-            Fe x0 = ld_fe_stream(T + j), x2 = ld_fe_stream(T + j + 2 * q);
-            lo[k] = fe_fold<F>(x0, x2, r);
-            st_fe(T + j, lo[k]);
-            Fe x1 = ld_fe_stream(T + j + q), x3 = ld_fe_stream(T + j + 3 * q);
-            hi[k] = fe_fold<F>(x1, x3, r);
-            st_fe(T + j + q, hi[k]);
+                    for (int t = 2; t <= D; t++) {
+                        hi = fe_add<F>(hi, d);
+                        pr[t] = hi;
+                    }
+                }
+            } else {
+                pr[0] = fe_mul<F>(lo, pr[0]);
+                if (D >= 2) lo = fe_sub<F>(hi, lo);  // lo := d
+                if (D >= 1) pr[1] = fe_mul<F>(hi, pr[1]);
+#pragma unroll
+                for (int t = 2; t <= D; t++) {
+                    hi = fe_add<F>(hi, lo);
+                    pr[t] = fe_mul<F>(hi, pr[t]);
+                }
+            }
         }
-        accumulate_products<F, M, D>(lo, hi, acc);
+#pragma unroll
+        for (int t = 0; t <= D; t++) acc[t] = fe_add<F>(acc[t], pr[t]);
     }
     reduce_publish<F, D + 1>(acc, ra);
 }
@@ -250,19 +238,23 @@ inline ReduceArgs make_ra(const ReduceScratch& s, int slot) {
 template <class F>
 Fe small_constant(unsigned t);  // Montgomery form of small integer t (host side)
 
-template <class F, int M, int D>
-cudaError_t do_round_poly(const TablePtrs& tabs, uint64_t half, const ReduceScratch& s, cudaStream_t st) {
-    static int bpsm = blocks_per_sm(round_poly_kernel<F, M, D>, kThreads);
-    unsigned grid = grid_for(half, kThreads, s.num_sms, bpsm);
-    round_poly_kernel<F, M, D><<<grid, kThreads, 0, st>>>(tabs, half, make_ra(s, 0));
+template <class F, int D, bool FOLD>
+cudaError_t do_round(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st) {
+    static int bpsm = blocks_per_sm(round_kernel<F, D, FOLD>, kThreads);
+    unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
+    round_kernel<F, D, FOLD><<<grid, kThreads, 0, st>>>(tabs, m, q, r, make_ra(s, 0));
     return cudaGetLastError();
 }
-template <class F, int M, int D>
-cudaError_t do_fold_round_poly(const TablePtrs& tabs, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st) {
-    static int bpsm = blocks_per_sm(fold_round_poly_kernel<F, M, D>, kThreads);
-    unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
-    fold_round_poly_kernel<F, M, D><<<grid, kThreads, 0, st>>>(tabs, q, r, make_ra(s, 0));
-    return cudaGetLastError();
+template <class F, bool FOLD>
+cudaError_t do_round_deg(const TablePtrs& tabs, int m, int degree, uint64_t q, const Fe& r, const ReduceScratch& s,
+                         cudaStream_t st) {
+    switch (degree) {
+        case 1: return do_round<F, 1, FOLD>(tabs, m, q, r, s, st);
+        case 2: return do_round<F, 2, FOLD>(tabs, m, q, r, s, st);
+        case 3: return do_round<F, 3, FOLD>(tabs, m, q, r, s, st);
+        case 4: return do_round<F, 4, FOLD>(tabs, m, q, r, s, st);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 // host-side Montgomery form of a small integer: t * R mod p by repeated addition of R (t <= kMaxDegree)
@@ -286,9 +278,7 @@ Fe host_small_mont(unsigned t) {
 template <class F>
 cudaError_t round_poly_dispatch(const TablePtrs& tabs, int m, int degree, uint64_t half, const ReduceScratch& s,
                                 cudaStream_t st, int* launches) {
-    if (m == 1 && degree == 1) { ++*launches; return do_round_poly<F, 1, 1>(tabs, half, s, st); }
-    if (m == 2 && degree == 2) { ++*launches; return do_round_poly<F, 2, 2>(tabs, half, s, st); }
-    if (m == 3 && degree == 3) { ++*launches; return do_round_poly<F, 3, 3>(tabs, half, s, st); }
+    if (has_fused_path(m, degree)) { ++*launches; return do_round_deg<F, false>(tabs, m, degree, half, Fe{}, s, st); }
     static int bpsm = blocks_per_sm(eval_at_kernel<F>, kThreads);
     unsigned grid = grid_for(half, kThreads, s.num_sms, bpsm);
     for (int t = 0; t <= degree; t++) {
@@ -314,9 +304,7 @@ template <class F>
 cudaError_t fold_round_poly_dispatch(const TablePtrs& tabs, int m, int degree, uint64_t n_prev, const Fe& r,
                                      const ReduceScratch& s, cudaStream_t st, int* launches) {
     const uint64_t q = n_prev / 4;
-    if (m == 1 && degree == 1) { ++*launches; return do_fold_round_poly<F, 1, 1>(tabs, q, r, s, st); }
-    if (m == 2 && degree == 2) { ++*launches; return do_fold_round_poly<F, 2, 2>(tabs, q, r, s, st); }
-    if (m == 3 && degree == 3) { ++*launches; return do_fold_round_poly<F, 3, 3>(tabs, q, r, s, st); }
+    if (has_fused_path(m, degree)) { ++*launches; return do_round_deg<F, true>(tabs, m, degree, q, r, s, st); }
     cudaError_t e = fold_dispatch<F>(tabs, m, n_prev / 2, r, &s, st, launches);
     if (e != cudaSuccess) return e;
     return round_poly_dispatch<F>(tabs, m, degree, n_prev / 4, s, st, launches);
@@ -333,7 +321,7 @@ cudaError_t product_sum_dispatch(const TablePtrs& tabs, int m, uint64_t n, const
 
 }  // namespace
 
-bool has_fused_path(int m, int degree) { return m == degree && m >= 1 && m <= 3; }
+bool has_fused_path(int m, int degree) { return m >= 1 && m <= kMaxFactors && degree >= 1 && degree <= 4; }
 
 cudaError_t launch_round_poly(int field, const TablePtrs& tabs, int m, int degree, uint64_t half,
                               const ReduceScratch& scratch, cudaStream_t stream, int* launches) {
