@@ -290,7 +290,7 @@ def run_ours(args):
     achieved = fused_bytes / fused_s / 1e9
     fused_muls = (2 * m + (d + 1) * (m - 1)) * (local_n0 // 4)
     mb = ctx.microbench(FIELD)
-    roofline = {"bound": "hbm", "kernel": f"fold_round_poly_kernel<Fr381,{m},{d}> (first fused step)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": f"round_kernel<Fr381,{d},FOLD=true> (first fused fold+round-sum step, m={m})", "achieved": achieved,
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_src,
                 "traffic": None, "algorithmic_bytes_per_launch": fused_bytes, "launch_ms": fused_s * 1e3,
                 "int_pipe": {"field_mul_per_s": fused_muls / fused_s, "standalone_fe_mul_per_s_peak": mb["fe_mul_per_s"],
@@ -313,7 +313,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs, IMAD.WIDE)", "data": "synthetic",
         "config": workload_config(n, m, d, world), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "cpu_baseline": cpu, "prove_ms": ms_per_step, "proof_keccak": proof_digest,
-        "round_kernel_ms": [round(x, 4) for x in ctx.last_round_ms()], "microbench": mb,
+        "round_kernel_ms": [round(x, 4) for x in ctx.last_round_ms()], "step_ms": [round(x, 3) for x in step_ms], "microbench": mb,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

@@ -9,6 +9,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 echo "launch list exit $?"
 CMD1="python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e"
 $CMD1 > gpurun_out/plain1_${TAG}.json 2> gpurun_out/plain1_${TAG}.err &&
-ncu --set full --clock-control none --import-source on -k regex:fold_round_poly -c 1 -f -o gpurun_out/prof_${TAG} $CMD1 > gpurun_out/ncu_full_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:round_kernel -s 1 -c 1 -f -o gpurun_out/prof_${TAG} $CMD1 > gpurun_out/ncu_full_${TAG}.log 2>&1
 echo "full capture exit $?"
 ls -la gpurun_out | tail -12

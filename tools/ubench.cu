@@ -3,7 +3,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
-#include "../zk_b200/csrc/field.cuh"
+#include "field29.cuh"
 using namespace zk;
 
 constexpr int T = 256;
@@ -157,6 +157,117 @@ __global__ void __launch_bounds__(T) kI(uint32_t seed, uint32_t* sink) {
     if (s == 0x1234567) sink[0] = s;
 }
 
+// M: reduced-radix carry-free multiplier chains
+template <int ILP>
+__global__ void __launch_bounds__(T) kM(uint32_t seed, Fe* sink) {
+    Fe29 x[ILP], y;
+    for (int k = 0; k < 9; k++) y.l[k] = (seed * 77 + k * 1234567u) & kMask29;
+    for (int c = 0; c < ILP; c++) for (int k = 0; k < 9; k++) x[c].l[k] = (seed + threadIdx.x * 9 + k + c * 31) & kMask29;
+#pragma unroll 1
+    for (int it = 0; it < 256; it++) {
+#pragma unroll
+        for (int c = 0; c < ILP; c++) x[c] = mul29<Fr381>(x[c], y);
+    }
+    uint32_t s = 0; for (int c = 0; c < ILP; c++) for (int k = 0; k < 9; k++) s ^= x[c].l[k];
+    if (s == 0x1234567) sink[0].v[0] = s;
+}
+// correctness: mul29(a, 32*b) must equal fe_mul(a, b) for Montgomery-form words
+__device__ __forceinline__ uint64_t smix(uint64_t z) { z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL; z ^= z >> 27; z *= 0x94D049BB133111EBULL; z ^= z >> 31; return z; }
+template <class F>
+__global__ void kCheck(unsigned* bad, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fe a, b;
+    for (int l = 0; l < 4; l++) {
+        uint64_t u = smix(0x1234 + (uint64_t)i * 8 + l), v = smix(0x9876 + (uint64_t)i * 8 + l + 4);
+        if (l == 3) { u &= 0x0FFFFFFFFFFFFFFFULL; v &= 0x0FFFFFFFFFFFFFFFULL; }
+        a.v[2 * l] = (uint32_t)u; a.v[2 * l + 1] = (uint32_t)(u >> 32); b.v[2 * l] = (uint32_t)v; b.v[2 * l + 1] = (uint32_t)(v >> 32);
+    }
+    if (i == 0) { a = fe_zero<F>(); }
+    if (i == 1) { for (int k = 0; k < 8; k++) { a.v[k] = F::p(k); b.v[k] = F::p(k); } a.v[0] -= 1; b.v[0] -= 1; }  // p-1
+    Fe expect = fe_mul<F>(a, b);
+    Fe b32 = b;
+    for (int d = 0; d < 5; d++) b32 = fe_add<F>(b32, b32);
+    Fe29 y = mul29<F>(unpack29(a), unpack29(b32));
+    Fe got = fe_reduce_once<F>(pack29(y));
+    bool same = true;
+    for (int k = 0; k < 8; k++) same &= (got.v[k] == expect.v[k]);
+    // round trip of the regrouping
+    Fe rt = pack29(unpack29(a));
+    for (int k = 0; k < 8; k++) same &= (rt.v[k] == a.v[k]);
+    if (!same) atomicAdd(bad, 1u);
+}
+
+// W1: pure 32x32->64 products, operands data dependent (cannot be hoisted): IMAD.WIDE.U32 R, Rlo, Rhi, RZ
+__global__ void __launch_bounds__(T) kW1(uint32_t seed, uint64_t* sink) {
+    uint64_t a[8]; for (int i = 0; i < 8; i++) a[i] = ((uint64_t)(seed * 77 + i) << 32) | (seed + threadIdx.x + i);
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) asm volatile("{.reg .u32 lo, hi; mov.b64 {lo, hi}, %0; mul.wide.u32 %0, lo, hi;}" : "+l"(a[i]));
+    }
+    uint64_t s = 0; for (int i = 0; i < 8; i++) s ^= a[i];
+    if (s == 0x1234567) sink[0] = s;
+}
+// W2: accumulate form with a data-dependent multiplicand: mad.wide.u32 acc, acc.lo, y, acc
+__global__ void __launch_bounds__(T) kW2(uint32_t seed, uint64_t* sink) {
+    uint64_t a[8]; for (int i = 0; i < 8; i++) a[i] = ((uint64_t)(seed * 77 + i) << 32) | (seed + threadIdx.x + i);
+    uint32_t y = seed * 2654435761u + threadIdx.x;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) asm volatile("{.reg .u32 lo, hi; mov.b64 {lo, hi}, %0; mad.wide.u32 %0, lo, %1, %0;}" : "+l"(a[i]) : "r"(y));
+    }
+    uint64_t s = 0; for (int i = 0; i < 8; i++) s ^= a[i];
+    if (s == 0x1234567) sink[0] = s;
+}
+// W3: 32-bit IMAD (lo) with data-dependent multiplicand
+__global__ void __launch_bounds__(T) kW3(uint32_t seed, uint32_t* sink) {
+    uint32_t a[8]; for (int i = 0; i < 8; i++) a[i] = seed + threadIdx.x + i;
+    uint32_t y = seed * 2654435761u + threadIdx.x;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) asm volatile("mad.lo.u32 %0, %0, %1, %0;" : "+r"(a[i]) : "r"(y));
+    }
+    uint32_t s = 0; for (int i = 0; i < 8; i++) s ^= a[i];
+    if (s == 0x1234567) sink[0] = s;
+}
+// W4: IMAD.HI with data-dependent multiplicand
+__global__ void __launch_bounds__(T) kW4(uint32_t seed, uint32_t* sink) {
+    uint32_t a[8]; for (int i = 0; i < 8; i++) a[i] = seed * 0x9e3779b9u + threadIdx.x + i;
+    uint32_t y = seed * 2654435761u + threadIdx.x;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) asm volatile("mad.hi.u32 %0, %0, %1, %0;" : "+r"(a[i]) : "r"(y));
+    }
+    uint32_t s = 0; for (int i = 0; i < 8; i++) s ^= a[i];
+    if (s == 0x1234567) sink[0] = s;
+}
+// W5: FFMA for reference (fp32 pipe = fmaheavy + fmalite)
+__global__ void __launch_bounds__(T) kW5(uint32_t seed, float* sink) {
+    float a[8]; for (int i = 0; i < 8; i++) a[i] = 1.0f + (seed + threadIdx.x + i) * 1e-6f;
+    float y = 1.0f + seed * 1e-7f;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) asm volatile("fma.rn.f32 %0, %0, %1, %0;" : "+f"(a[i]) : "f"(y));
+    }
+    float s = 0; for (int i = 0; i < 8; i++) s += a[i];
+    if (s == 0.1234567f) sink[0] = s;
+}
+
 template <class L> float run(L&& launch) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;
@@ -168,11 +279,29 @@ int main() {
     int clk_khz = 0; cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
     void* sink; cudaMalloc(&sink, 256);
     const double sm_clk = 1.965e9 * sms;  // report per SM-clock at the max clock (nvidia-smi shows 1965 MHz under this load)
-    for (int bps : {4}) {
+    {
+        unsigned* bad; cudaMalloc(&bad, 4); cudaMemset(bad, 0, 4);
+        kCheck<Fr381><<<4096, 256>>>(bad, 1 << 20);
+        unsigned h381 = 0; cudaMemcpy(&h381, bad, 4, cudaMemcpyDeviceToHost); cudaMemset(bad, 0, 4);
+        kCheck<Fr377><<<4096, 256>>>(bad, 1 << 20);
+        unsigned h377 = 0; cudaMemcpy(&h377, bad, 4, cudaMemcpyDeviceToHost);
+        printf("mul29 vs fe_mul mismatches over 2^20 pairs: Fr381 %u, Fr377 %u  (%s)\n", h381, h377, cudaGetErrorString(cudaGetLastError()));
+    }
+    for (int bps : {4, 8}) {
         const int blocks = sms * bps; const double thr = (double)blocks * T;
         printf("--- %d blocks/SM x %d threads (%d warps/SMSP)\n", bps, T, bps * T / 32 / 4);
         float ms = run([&] { kA<<<blocks, T>>>(7, (uint64_t*)sink); });
         printf("A  IMAD.WIDE independent      : %7.2f instr/clk/SM\n", thr * ITERS * 32 / (ms * 1e-3) / sm_clk);
+        ms = run([&] { kW1<<<blocks, T>>>(7, (uint64_t*)sink); });
+        printf("W1 IMAD.WIDE product (dep ops): %7.2f instr/clk/SM\n", thr * ITERS * 32 / (ms * 1e-3) / sm_clk);
+        ms = run([&] { kW2<<<blocks, T>>>(7, (uint64_t*)sink); });
+        printf("W2 mad.wide accumulate (dep)  : %7.2f instr/clk/SM\n", thr * ITERS * 32 / (ms * 1e-3) / sm_clk);
+        ms = run([&] { kW3<<<blocks, T>>>(7, (uint32_t*)sink); });
+        printf("W3 IMAD lo (dep)              : %7.2f instr/clk/SM\n", thr * ITERS * 32 / (ms * 1e-3) / sm_clk);
+        ms = run([&] { kW4<<<blocks, T>>>(7, (uint32_t*)sink); });
+        printf("W4 IMAD.HI (dep)              : %7.2f instr/clk/SM\n", thr * ITERS * 32 / (ms * 1e-3) / sm_clk);
+        ms = run([&] { kW5<<<blocks, T>>>(7, (float*)sink); });
+        printf("W5 FFMA (dep)                 : %7.2f instr/clk/SM\n", thr * ITERS * 32 / (ms * 1e-3) / sm_clk);
         ms = run([&] { kB<1><<<blocks, T>>>(7, (uint32_t*)sink); });
         printf("B1 cmad4 chain x1 (4W.X+addc) : %7.2f WIDE/clk/SM\n", thr * ITERS * 2 * 1 * 4 / (ms * 1e-3) / sm_clk);
         ms = run([&] { kB<2><<<blocks, T>>>(7, (uint32_t*)sink); });
@@ -191,6 +320,10 @@ int main() {
         printf("H8 add.cc + WIDE carry-in     : %7.2f WIDE/clk/SM\n", thr * ITERS * 4 * 8 / (ms * 1e-3) / sm_clk);
         ms = run([&] { kI<<<blocks, T>>>(7, (uint32_t*)sink); });
         printf("I  IADD3 (3-input) independent: %7.2f instr/clk/SM\n", thr * ITERS * 32 / (ms * 1e-3) / sm_clk);
+        ms = run([&] { kM<1><<<blocks, T>>>(7, (Fe*)sink); });
+        printf("M1 mul29 ILP1                 : %7.3f mul/clk/SM  (%.3e mul/s)\n", thr * 256 * 1 / (ms * 1e-3) / sm_clk, thr * 256 * 1 / (ms * 1e-3));
+        ms = run([&] { kM<2><<<blocks, T>>>(7, (Fe*)sink); });
+        printf("M2 mul29 ILP2                 : %7.3f mul/clk/SM  (%.3e mul/s)\n", thr * 256 * 2 / (ms * 1e-3) / sm_clk, thr * 256 * 2 / (ms * 1e-3));
         ms = run([&] { kE<1, false><<<blocks, T>>>(7, (Fe*)sink); });
         printf("E1 fe_mul ILP1                : %7.3f mul/clk/SM  (%.3e mul/s)\n", thr * 256 * 1 / (ms * 1e-3) / sm_clk, thr * 256 * 1 / (ms * 1e-3));
         ms = run([&] { kE<2, false><<<blocks, T>>>(7, (Fe*)sink); });

@@ -647,6 +647,16 @@ int absorb_tables(zk_ctx* ctx, const zk_table* const* tables, unsigned m, zk::ho
     return st;
 }
 
+// Env-gated per-phase log in the spirit of the reference's `stat` crate (stat/src/lib.rs:12-30, PERF_LOG=true).
+bool perf_log_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("PERF_LOG");
+        v = (e && std::strcmp(e, "true") == 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+
 struct ProveTimer {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     double ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
@@ -726,11 +736,23 @@ int zk_sumcheck_prove(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
         }
         cudaError_t e = timed([&] { return zk::launch_round_poly(field, cur, (int)m, (int)degree, cur_len / 2, ctx->scratch, ctx->stream, &ctx->launches); });
         if (e != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "round_poly"); }
+        if (perf_log_enabled()) {
+            cudaStreamSynchronize(ctx->stream);
+            std::fprintf(stderr, "[zk_b200 rank %d] round 0 kernel done at %.3f ms\n", ctx->rank, timer.ms());
+        }
         st = finish_reduction(ctx, field, np, S.data(), sharded);
         if (st != ZK_OK) { cleanup(); return st; }
+        if (perf_log_enabled()) std::fprintf(stderr, "[zk_b200 rank %d] round 0 reduced at %.3f ms\n", ctx->rank, timer.ms());
     }
     El r = F.zero();
+    double t_prev = timer.ms();
     for (unsigned round = 0; round < n; round++) {
+        if (perf_log_enabled()) {
+            double t_now = timer.ms();
+            std::fprintf(stderr, "[zk_b200 rank %d] round %u: table 2^%u%s, %.3f ms since previous round\n", ctx->rank, round,
+                         log2_exact(cur_len), sharded ? " (sharded)" : "", t_now - t_prev);
+            t_prev = t_now;
+        }
         std::memcpy(round_polys_out + (size_t)round * np * 4, S.data(), (size_t)np * 32);
         for (int t = 0; t < np; t++) tr.append_element(F, el_from(S.data() + 4 * t));  // prover.rs:59
         r = tr.sample_field_element(F);                                                // prover.rs:62

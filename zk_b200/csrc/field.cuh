@@ -10,7 +10,7 @@
 // rows ("even" columns / "odd" columns) so that every 32x32->64 partial product lands on an aligned
 // register pair and the whole row is ONE carry chain: ptxas lowers each mad.lo.cc/madc.hi.cc pair to
 // a single IMAD.WIDE.U32(.X) with predicate carries.  Both supported moduli are == 1 (mod 2^32), so
-// the per-row Montgomery factor is m = -t0 (no multiply).
+// the per-row Montgomery factor is m = -t0 (no multiply) and m*p_0 needs no multiply either.
 #pragma once
 #include <cstdint>
 
@@ -232,11 +232,49 @@ __device__ __forceinline__ void madc4_rshift(uint32_t* Y, uint32_t& x0, uint32_t
         : "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7]), "+r"(x0)
         : "r"(a1), "r"(a3), "r"(a5), "r"(a7), "r"(b));
 }
+// Reduction half-rows.  Both moduli have p_0 = 1, so X[0] + m*p_0 is just X[0] + m = 0 with carry
+// (X[0] != 0): two carry adds instead of a multiply.  For BLS12-381 Fr also p_1 = 2^32 - 1, and
+// m*(2^32-1) = ((m - c) << 32) + t0 with t0 = -m, c = (t0 != 0): two more adds instead of a multiply.
+// IMAD.WIDE.U32 issues at half the IMAD rate on sm_100a (32 per clock per SM, measured) and is the
+// binding pipe of every kernel here while the ALU pipe idles, so: 112 (381) / 120 (377) wide multiplies
+// per field multiplication instead of 128.
+__device__ __forceinline__ void redc_even(uint32_t* X, uint32_t m, uint32_t p2, uint32_t p4, uint32_t p6,
+                                          uint32_t& top) {
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "madc.lo.cc.u32 %2, %10, %9, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %9, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %9, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %9, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %9, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %9, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(top)
+        : "r"(m), "r"(p2), "r"(p4), "r"(p6));
+}
+// Y += m * (p1, p3, p5, p7) with p1 = 2^32 - 1: (Y1:Y0) += ((m - c) : t0)
+__device__ __forceinline__ void redc_odd_p1allones(uint32_t* Y, uint32_t m, uint32_t t0, uint32_t p3, uint32_t p5,
+                                                   uint32_t p7) {
+    uint32_t c, hi;
+    asm("min.u32 %0, %1, 1;" : "=r"(c) : "r"(t0));
+    hi = m - c;
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, %10;\n\t"
+        "madc.lo.cc.u32 %2, %11, %8, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %8, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %8, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %8, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %8, %6;\n\t"
+        "madc.hi.u32 %7, %13, %8, %7;"
+        : "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7])
+        : "r"(m), "r"(t0), "r"(hi), "r"(p3), "r"(p5), "r"(p7));
+}
 // One operand-scanning row: (X | Y) += a * b ; then += m * p with m = -X[0] so that column 0 clears.
 // X holds columns 0..7 ((0,1),(2,3),.. product pairs), Y holds columns 1..8.  After the row the
 // roles swap (the caller alternates the arguments), which is the division by 2^32.
 template <class F>
 __device__ __forceinline__ void mont_row(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t b, bool first) {
+    static_assert(F::p(0) == 1u, "the reduction rows assume p == 1 (mod 2^32)");
     if (first) {
         mul4(Y, a[1], a[3], a[5], a[7], b);
         mul4(X, a[0], a[2], a[4], a[6], b);
@@ -246,12 +284,16 @@ __device__ __forceinline__ void mont_row(uint32_t* X, uint32_t* Y, const uint32_
     }
     // m = -X[0]: -p^-1 mod 2^32 == 0xffffffff for both moduli.  Kept opaque (asm volatile): if the
     // optimizer sees the negation it folds it into the multiply-adds below and ptxas then emits split
-    // IMAD.X + IMAD.HI.U32.X pairs (2 FMA-pipe slots per product) instead of one IMAD.WIDE.U32.X.
+    // IMAD.X + IMAD.HI.U32.X pairs instead of one IMAD.WIDE.U32.X per product.
+    const uint32_t t0 = X[0];
     uint32_t m;
-    asm volatile("sub.u32 %0, 0, %1;" : "=r"(m) : "r"(X[0]));
+    asm volatile("sub.u32 %0, 0, %1;" : "=r"(m) : "r"(t0));
     // total value stays < 2^288 (a < p), so the Y chain never carries out of column 8
-    cmad4_nocarry(Y, F::p(1), F::p(3), F::p(5), F::p(7), m);
-    cmad4(X, F::p(0), F::p(2), F::p(4), F::p(6), m, Y[7]);
+    if (F::p(1) == 0xffffffffu)
+        redc_odd_p1allones(Y, m, t0, F::p(3), F::p(5), F::p(7));
+    else
+        cmad4_nocarry(Y, F::p(1), F::p(3), F::p(5), F::p(7), m);
+    redc_even(X, m, F::p(2), F::p(4), F::p(6), Y[7]);
 }
 }  // namespace detail
 

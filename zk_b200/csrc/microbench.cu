@@ -19,9 +19,13 @@ __global__ void __launch_bounds__(kThreads) imad_wide_kernel(uint32_t seed, uint
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             asm volatile(
-                "mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\tmad.wide.u32 %2, %8, %9, %2;\n\t"
-                "mad.wide.u32 %3, %8, %9, %3;\n\tmad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\t"
-                "mad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
+                // operands are the halves of the running value, so nothing is loop invariant (a loop-invariant
+                // product is hoisted by ptxas and the probe then measures 64-bit adds, not multiplies)
+                "{.reg .u32 l, h;\n\t"
+                "mov.b64 {l,h}, %0; mul.wide.u32 %0, l, h;\n\tmov.b64 {l,h}, %1; mul.wide.u32 %1, l, h;\n\t"
+                "mov.b64 {l,h}, %2; mul.wide.u32 %2, l, h;\n\tmov.b64 {l,h}, %3; mul.wide.u32 %3, l, h;\n\t"
+                "mov.b64 {l,h}, %4; mul.wide.u32 %4, l, h;\n\tmov.b64 {l,h}, %5; mul.wide.u32 %5, l, h;\n\t"
+                "mov.b64 {l,h}, %6; mul.wide.u32 %6, l, h;\n\tmov.b64 {l,h}, %7; mul.wide.u32 %7, l, h;}"
                 : "+l"(a0), "+l"(a1), "+l"(a2), "+l"(a3), "+l"(a4), "+l"(a5), "+l"(a6), "+l"(a7)
                 : "r"(x), "r"(y));
         }
@@ -39,9 +43,9 @@ __global__ void __launch_bounds__(kThreads) imad_lo_kernel(uint32_t seed, uint32
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             asm volatile(
-                "mad.lo.u32 %0, %8, %9, %0;\n\tmad.lo.u32 %1, %8, %9, %1;\n\tmad.lo.u32 %2, %8, %9, %2;\n\t"
-                "mad.lo.u32 %3, %8, %9, %3;\n\tmad.lo.u32 %4, %8, %9, %4;\n\tmad.lo.u32 %5, %8, %9, %5;\n\t"
-                "mad.lo.u32 %6, %8, %9, %6;\n\tmad.lo.u32 %7, %8, %9, %7;"
+                "mad.lo.u32 %0, %0, %9, %0;\n\tmad.lo.u32 %1, %1, %9, %1;\n\tmad.lo.u32 %2, %2, %9, %2;\n\t"
+                "mad.lo.u32 %3, %3, %9, %3;\n\tmad.lo.u32 %4, %4, %9, %4;\n\tmad.lo.u32 %5, %5, %9, %5;\n\t"
+                "mad.lo.u32 %6, %6, %9, %6;\n\tmad.lo.u32 %7, %7, %9, %7;"
                 : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7)
                 : "r"(x), "r"(y));
         }
@@ -75,8 +79,9 @@ __global__ void __launch_bounds__(kThreads) mixed_kernel(uint32_t seed, uint64_t
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             asm volatile(
-                "mad.wide.u32 %0, %8, %9, %0;\n\tadd.u32 %4, %4, %8;\n\tmad.wide.u32 %1, %8, %9, %1;\n\tadd.u32 %5, %5, %8;\n\t"
-                "mad.wide.u32 %2, %8, %9, %2;\n\tadd.u32 %6, %6, %8;\n\tmad.wide.u32 %3, %8, %9, %3;\n\tadd.u32 %7, %7, %8;"
+                "{.reg .u32 l, h;\n\t"
+                "mov.b64 {l,h}, %0; mul.wide.u32 %0, l, h;\n\tadd.u32 %4, %4, %8;\n\tmov.b64 {l,h}, %1; mul.wide.u32 %1, l, h;\n\tadd.u32 %5, %5, %8;\n\t"
+                "mov.b64 {l,h}, %2; mul.wide.u32 %2, l, h;\n\tadd.u32 %6, %6, %8;\n\tmov.b64 {l,h}, %3; mul.wide.u32 %3, l, h;\n\tadd.u32 %7, %7, %8;}"
                 : "+l"(a0), "+l"(a1), "+l"(a2), "+l"(a3), "+r"(b0), "+r"(b1), "+r"(b2), "+r"(b3)
                 : "r"(x), "r"(y));
         }
