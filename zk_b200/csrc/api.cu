@@ -72,6 +72,7 @@ struct zk_ctx {
     std::vector<cudaEvent_t> events;
     std::vector<float> round_ms;
     double prove_ms[3] = {0, 0, 0};
+    std::vector<zk::NttPlan*> ntt_plans;  // small cache: twiddle tables are reused across calls
 };
 
 struct zk_table {
@@ -285,6 +286,7 @@ void zk_ctx_destroy(zk_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm) nccl().CommDestroy(c->comm);
+    for (auto* pl : c->ntt_plans) zk::ntt_plan_destroy(pl);
     for (auto ev : c->events) cudaEventDestroy(ev);
     cudaFree(c->scratch.block_partials);
     cudaFree(c->scratch.ticket);
@@ -975,11 +977,20 @@ int zk_ntt(zk_ctx* ctx, zk_table* inout, int inverse) {
     CU(ctx, cudaSetDevice(ctx->device));
     if (inout->n_vars == 0) return ZK_OK;  // fft_internal: len == 1 -> unchanged (ifft scales by 1^-1 = 1)
     zk::NttPlan* plan = nullptr;
-    cudaError_t e = zk::ntt_plan_create(inout->field, inout->n_vars, inverse != 0, ctx->stream, &plan, &ctx->launches);
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "ntt_plan_create");
+    for (auto* pl : ctx->ntt_plans)
+        if (zk::ntt_plan_is(pl, inout->field, inout->n_vars, inverse != 0)) plan = pl;
+    cudaError_t e = cudaSuccess;
+    if (!plan) {
+        if (ctx->ntt_plans.size() >= 2) {  // keep at most a forward/inverse pair resident
+            for (auto* pl : ctx->ntt_plans) zk::ntt_plan_destroy(pl);
+            ctx->ntt_plans.clear();
+        }
+        e = zk::ntt_plan_create(inout->field, inout->n_vars, inverse != 0, ctx->stream, &plan, &ctx->launches);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "ntt_plan_create");
+        ctx->ntt_plans.push_back(plan);
+    }
     e = zk::ntt_execute(plan, inout->data, ctx->stream, &ctx->launches);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    zk::ntt_plan_destroy(plan);
     count(ctx);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "ntt_execute");
     return ZK_OK;

@@ -76,6 +76,7 @@ cudaError_t launch_narrow(int field, const uint64_t* lanes, Fe* out_dev, Fe* out
 struct NttPlan;
 cudaError_t ntt_plan_create(int field, unsigned log_n, bool inverse, cudaStream_t stream, NttPlan** out, int* launches);
 void ntt_plan_destroy(NttPlan*);
+bool ntt_plan_is(const NttPlan*, int field, unsigned log_n, bool inverse);
 // natural order in -> natural order out, in place on `data` (uses plan-owned scratch)
 cudaError_t ntt_execute(NttPlan* plan, Fe* data, cudaStream_t stream, int* launches);
 

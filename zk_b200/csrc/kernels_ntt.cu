@@ -5,7 +5,11 @@
 // The reference recurses with fresh vectors, recomputes `omega.pow([i])` twice per butterfly and
 // inverts N once per output element; here twiddles w^i (i < N/2) are built once per plan by doubling,
 // the transform is log2(N) decimation-in-frequency stages (one twiddle multiplication per butterfly,
-// X - Y*w reuses the product) followed by one bit-reversal pass that also applies N^-1.
+// X - Y*w reuses the product) followed by one bit-reversal pass that also applies N^-1.  Stages are grouped
+// into passes of up to 9: a pass loads tiles of 2^s elements (stride N_b/2^s, 4 adjacent tiles per block so
+// global accesses are 128-byte segments) into shared memory, runs a plain 2^s-point DIF there with the small
+// twiddles w_{2^s}^j, multiplies output c by the inter-pass twiddle w_N^(2^t0 * base * c) and writes back in
+// place (the classic four-step factorisation).  2^28 points: 4 passes over the data instead of 28.
 // Any exact algorithm gives bit-identical outputs (integer arithmetic).
 #include "keccak.hpp"  // host_field.hpp
 #include "kernels.h"
@@ -67,6 +71,83 @@ __global__ void __launch_bounds__(kThreads) bitrev_kernel(Fe* a, uint64_t n, uns
     }
 }
 
+
+// ---- shared-memory pass: s consecutive DIF stages starting at stage t0 ------------------------------
+constexpr int kTileB = 4;          // adjacent tiles per block (128-byte global segments)
+constexpr int kMaxTileLog = 9;     // 2^9 * 4 * 32 B = 64 KB of shared memory per block
+constexpr int kPassThreads = 256;
+
+__device__ __forceinline__ Fe lds_fe(const uint4* lo, const uint4* hi, unsigned i) {
+    uint4 a = lo[i], b = hi[i];
+    Fe r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void sts_fe(uint4* lo, uint4* hi, unsigned i, const Fe& r) {
+    lo[i] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    hi[i] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+template <class F>
+__global__ void __launch_bounds__(kPassThreads)
+    ntt_pass_kernel(Fe* a, const Fe* __restrict__ tw, unsigned log_n, unsigned t0, unsigned s, uint64_t n_groups) {
+    extern __shared__ uint4 smem[];
+    const unsigned tile = 1u << s, elems = tile * kTileB;
+    uint4* lo = smem;                 // [elems]   limbs 0-3 of element (x, b) at x*kTileB + b
+    uint4* hi = smem + elems;         // [elems]   limbs 4-7
+    uint4* wlo = smem + 2 * elems;    // [tile/2]  small twiddles w_{2^s}^j
+    uint4* whi = wlo + (tile >> 1);
+    const unsigned log_nb = log_n - t0;                  // this pass works inside blocks of 2^log_nb
+    const unsigned log_stride = log_nb - s;              // distance between consecutive tile elements
+    const uint64_t stride = (uint64_t)1 << log_stride;
+    const bool b_fastest = stride >= kTileB;             // which index walks contiguous memory
+    for (unsigned j = threadIdx.x; j < (tile >> 1); j += kPassThreads)
+        sts_fe(wlo, whi, j, ld_fe(tw + ((uint64_t)j << (log_n - s))));
+    for (uint64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const uint64_t tile0 = g * kTileB;               // first of kTileB consecutive tile ids
+        __syncthreads();
+        // ---- load ----
+        for (unsigned e = threadIdx.x; e < elems; e += kPassThreads) {
+            unsigned x, b;
+            if (b_fastest) { b = e % kTileB; x = e / kTileB; } else { x = e % tile; b = e / tile; }
+            const uint64_t t = tile0 + b, blk = t >> log_stride, base = t & (stride - 1);
+            sts_fe(lo, hi, x * kTileB + b, ld_fe_stream(a + (blk << log_nb) + base + ((uint64_t)x << log_stride)));
+        }
+        __syncthreads();
+        // ---- s DIF stages in shared memory ----
+        for (unsigned u = 0; u < s; u++) {
+            const unsigned log_half = s - 1 - u, half = 1u << log_half;
+            for (unsigned q = threadIdx.x; q < (elems >> 1); q += kPassThreads) {
+                const unsigned b = q % kTileB, j = q / kTileB, jl = j & (half - 1);
+                const unsigned x0 = ((j >> log_half) << (log_half + 1)) | jl, x1 = x0 + half;
+                Fe p = lds_fe(lo, hi, x0 * kTileB + b), v = lds_fe(lo, hi, x1 * kTileB + b);
+                sts_fe(lo, hi, x0 * kTileB + b, fe_add<F>(p, v));
+                Fe d = fe_sub<F>(p, v);
+                if (jl != 0) d = fe_mul<F>(d, lds_fe(wlo, whi, jl << u));
+                sts_fe(lo, hi, x1 * kTileB + b, d);
+            }
+            __syncthreads();
+        }
+        // ---- inter-pass twiddle + store (in place) ----
+        for (unsigned e = threadIdx.x; e < elems; e += kPassThreads) {
+            unsigned x, b;
+            if (b_fastest) { b = e % kTileB; x = e / kTileB; } else { x = e % tile; b = e / tile; }
+            const uint64_t t = tile0 + b, blk = t >> log_stride, base = t & (stride - 1);
+            Fe val = lds_fe(lo, hi, x * kTileB + b);
+            if (log_stride != 0) {
+                const uint64_t c = __brev(x) >> (32 - s);                  // position x holds output c = bitrev_s(x)
+                const uint64_t ex = (base * c) << t0, half_n = (uint64_t)1 << (log_n - 1);
+                if (ex != 0) {
+                    if (ex >= half_n) val = fe_sub<F>(fe_zero<F>(), fe_mul<F>(val, ld_fe(tw + (ex - half_n))));
+                    else val = fe_mul<F>(val, ld_fe(tw + ex));
+                }
+            }
+            st_fe(a + (blk << log_nb) + base + ((uint64_t)x << log_stride), val);
+        }
+    }
+}
+
 template <class F>
 cudaError_t plan_build(NttPlan* p, cudaStream_t st, int* launches) {
     host::Field HF(F::ID);
@@ -97,14 +178,41 @@ cudaError_t plan_build(NttPlan* p, cudaStream_t st, int* launches) {
 
 template <class F>
 cudaError_t execute(NttPlan* p, Fe* data, cudaStream_t st, int* launches) {
-    const uint64_t n = (uint64_t)1 << p->log_n, n_half = n >> 1;
-    for (unsigned s = 0; s < p->log_n; s++) {
-        dif_stage_kernel<F><<<grid_1d(n_half), kThreads, 0, st>>>(data, p->twiddles, n_half, p->log_n - 1 - s, s);
-        ++*launches;
+    const unsigned k = p->log_n;
+    const uint64_t n = (uint64_t)1 << k;
+    // split the k stages into ceil(k/9) passes of (almost) equal size, every pass >= 2 stages when k >= 4
+    const unsigned n_pass = (k + kMaxTileLog - 1) / kMaxTileLog;
+    static bool attr_set = false;
+    const size_t max_smem = (size_t)(2 * ((1u << kMaxTileLog) * kTileB) + (1u << kMaxTileLog)) * sizeof(uint4);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    unsigned t0 = 0;
+    for (unsigned pi = 0; pi < n_pass; pi++) {
+        const unsigned s = (k - t0) / (n_pass - pi);       // remaining stages spread over remaining passes
+        const uint64_t n_tiles = n >> s;
+        if (n_tiles < kTileB) {                            // tiny transform: the per-stage kernel is enough
+            for (unsigned t = t0; t < t0 + s; t++) {
+                dif_stage_kernel<F><<<grid_1d(n >> 1), kThreads, 0, st>>>(data, p->twiddles, n >> 1, k - 1 - t, t);
+                ++*launches;
+            }
+        } else {
+            const uint64_t n_groups = n_tiles / kTileB;
+            const size_t smem = (size_t)(2 * ((1u << s) * kTileB) + (1u << s)) * sizeof(uint4);
+            const unsigned grid = (unsigned)(n_groups < (uint64_t)sms * 3 ? n_groups : (uint64_t)sms * 3);
+            ntt_pass_kernel<F><<<grid, kPassThreads, smem, st>>>(data, p->twiddles, k, t0, s, n_groups);
+            ++*launches;
+        }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
+        t0 += s;
     }
-    bitrev_kernel<F><<<grid_1d(n), kThreads, 0, st>>>(data, n, p->log_n, p->inverse, p->n_inv);
+    bitrev_kernel<F><<<grid_1d(n), kThreads, 0, st>>>(data, n, k, p->inverse, p->n_inv);
     ++*launches;
     return cudaGetLastError();
 }
@@ -119,6 +227,9 @@ cudaError_t ntt_plan_create(int field, unsigned log_n, bool inverse, cudaStream_
     }
     *out = p;
     return cudaSuccess;
+}
+bool ntt_plan_is(const NttPlan* p, int field, unsigned log_n, bool inverse) {
+    return p && p->field == field && p->log_n == log_n && p->inverse == inverse;
 }
 void ntt_plan_destroy(NttPlan* p) {
     if (!p) return;
