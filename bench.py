@@ -55,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -204,12 +204,15 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     step_ms, fused_ms, launches0 = [], [], None
     wall_t0 = wall_t1 = None
+    tabs = gen_tables()
     for it in range(args.warmup + args.steps):
-        tabs = gen_tables()  # untimed: prove consumes its tables
+        if it:  # untimed: prove consumes its tables, refill the same allocations
+            for k in range(m):
+                tabs[k].regenerate(k, seed=SEED)
         timed = it >= args.warmup
+        if it == 0 and rank == 0:
+            sampler.start()  # started before the warm-up so that nvidia-smi/NVML initialisation is not inside the timed steps
         if timed and launches0 is None:
-            sampler.start()
-            time.sleep(0.25)
             launches0 = ctx.launch_count()
             wall_t0 = time.time()
         barrier()
@@ -222,10 +225,10 @@ def run_ours(args):
             step_ms.append(e0.elapsed_time(e1))
             r = ctx.last_round_ms()
             fused_ms.append(r[1] if len(r) > 1 else r[0])
-        del tabs
+    del tabs
     wall_t1 = time.time()
-    launches = ctx.launch_count() - launches0 - args.steps * m  # minus the (untimed) generator launches
-    clocks = sampler.stop(wall_t0, wall_t1)
+    launches = ctx.launch_count() - launches0 - (args.steps - (1 if args.warmup == 0 else 0)) * m  # minus the (untimed) generator launches
+    clocks = sampler.stop(wall_t0, wall_t1) if rank == 0 else None
     proof_digest = zk.keccak256(rp.tobytes() + ch.tobytes()).hex()
     # the reference verifier's own checks on the last proof (host side, sumcheck/src/verifier.rs:44-78):
     # every round check passes, the replayed challenges equal the prover's, and the subclaim equals the

@@ -105,6 +105,8 @@ ZK_API int zk_host_free(void* p);
 ZK_API int zk_table_upload(zk_ctx* ctx, int field, const uint64_t* mont_aos, uint64_t len, unsigned n_vars, zk_table** out);
 /* Deterministic synthetic table `table_id` (SURVEY.md 8d generator), generated on the device by global index. */
 ZK_API int zk_table_generate(zk_ctx* ctx, int field, uint64_t seed, uint64_t table_id, unsigned n_vars, zk_table** out);
+/* Refill an existing table (e.g. one consumed by zk_sumcheck_prove) with synthetic table `table_id`: no allocation. */
+ZK_API int zk_table_regenerate(zk_ctx* ctx, zk_table* t, uint64_t seed, uint64_t table_id);
 ZK_API int zk_table_clone(zk_ctx* ctx, const zk_table* in, zk_table** out);
 ZK_API void zk_table_free(zk_table* t);
 ZK_API unsigned zk_table_n_vars(const zk_table* t);     /* n_vars() :30 */

@@ -165,6 +165,10 @@ class MultiLinearPolynomial:
         ctx.check(lib().zk_table_generate(ctx.h, field, seed, table_id, n_vars, C.byref(h)))
         return cls(h, ctx)
 
+    def regenerate(self, table_id: int, seed: int = DEFAULT_SEED):
+        """Refill this table in place with synthetic table `table_id` (reuses the allocation)."""
+        self.ctx.check(lib().zk_table_regenerate(self.ctx.h, self._h, seed, table_id))
+
     def n_vars(self) -> int:  # :30
         return int(lib().zk_table_n_vars(self._h))
 

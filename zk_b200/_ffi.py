@@ -47,6 +47,7 @@ SIGNATURES = {
     "zk_host_free": (C.c_int, [vp]),
     "zk_table_upload": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_uint, vpp]),
     "zk_table_generate": (C.c_int, [vp, C.c_int, C.c_uint64, C.c_uint64, C.c_uint, vpp]),
+    "zk_table_regenerate": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64]),
     "zk_table_clone": (C.c_int, [vp, vp, vpp]),
     "zk_table_free": (None, [vp]),
     "zk_table_n_vars": (C.c_uint, [vp]),

@@ -379,6 +379,19 @@ int zk_table_generate(zk_ctx* ctx, int field, uint64_t seed, uint64_t table_id, 
     return ZK_OK;
 }
 
+int zk_table_regenerate(zk_ctx* ctx, zk_table* t, uint64_t seed, uint64_t table_id) {
+    if (!ctx || !t) return fail(ctx, ZK_ERR_INVALID_ARG);
+    CU(ctx, cudaSetDevice(ctx->device));
+    const uint64_t world = (uint64_t)ctx->world, local = ((uint64_t)1 << t->n_vars) / world;
+    if (local > t->capacity) return fail(ctx, ZK_ERR_INVALID_ARG, "table allocation too small");
+    t->local_len = local;
+    CU(ctx, zk::launch_generate(t->field, t->data, local, seed, table_id, (uint64_t)ctx->rank, world, ctx->stream,
+                                &ctx->launches));
+    count(ctx);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+
 int zk_table_clone(zk_ctx* ctx, const zk_table* in, zk_table** out) {
     if (!ctx || !in || !out) return fail(ctx, ZK_ERR_INVALID_ARG);
     CU(ctx, cudaSetDevice(ctx->device));
@@ -697,22 +710,22 @@ int zk_sumcheck_prove(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
     uint64_t cur_len = tables[0]->local_len;
     bool sharded = ctx->world > 1;
     std::vector<Fe*> gathered;  // owned buffers after the residual gather
-    auto cleanup = [&]() { for (Fe* p : gathered) cudaFree(p); };
+    auto cleanup = [&]() { for (Fe* p : gathered) cudaFreeAsync(p, ctx->stream); };
 
     // Gather the per-rank residual tables (local length L) into full tables of L*world entries on every rank.
     auto gather = [&]() -> int {
         const uint64_t L = cur_len, G = (uint64_t)ctx->world;
         for (unsigned k = 0; k < m; k++) {
+            // stream-ordered allocations: no device-wide synchronisation on the critical path
             Fe *stage = nullptr, *full = nullptr;
-            cudaError_t e = cudaMalloc((void**)&stage, (size_t)(L * G) * 32);
-            if (e == cudaSuccess) e = cudaMalloc((void**)&full, (size_t)(L * G) * 32);
-            if (e != cudaSuccess) { cudaFree(stage); return cuda_fail(ctx, e, "gather alloc"); }
+            cudaError_t e = cudaMallocAsync((void**)&stage, (size_t)(L * G) * 32, ctx->stream);
+            if (e == cudaSuccess) e = cudaMallocAsync((void**)&full, (size_t)(L * G) * 32, ctx->stream);
+            if (e != cudaSuccess) { if (stage) cudaFreeAsync(stage, ctx->stream); return cuda_fail(ctx, e, "gather alloc"); }
             int rc = nccl().AllGather(cur.t[k], stage, (size_t)L * 32, kNcclUint8, ctx->comm, ctx->stream);
-            if (rc != 0) { cudaFree(stage); cudaFree(full); return fail(ctx, ZK_ERR_NCCL, "allgather"); }
+            if (rc != 0) { cudaFreeAsync(stage, ctx->stream); cudaFreeAsync(full, ctx->stream); return fail(ctx, ZK_ERR_NCCL, "allgather"); }
             e = zk::launch_interleave(stage, full, L, (unsigned)G, ctx->stream, &ctx->launches);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            cudaFree(stage);
-            if (e != cudaSuccess) { cudaFree(full); return cuda_fail(ctx, e, "gather"); }
+            cudaFreeAsync(stage, ctx->stream);
+            if (e != cudaSuccess) { cudaFreeAsync(full, ctx->stream); return cuda_fail(ctx, e, "gather"); }
             gathered.push_back(full);
             cur.t[k] = full;
         }
