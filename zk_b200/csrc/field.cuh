@@ -41,6 +41,11 @@ struct Fr381 {
                                    0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
         return t[i];
     }
+    __host__ __device__ static constexpr uint32_t k288(int i) {  // 2^288 mod p (plain integer)
+        constexpr uint32_t t[8] = {0xcaaf6b13u, 0x355094eau, 0x69a568efu, 0xf6b10cb3u,
+                                   0x40cc3869u, 0xe2c926a6u, 0xed269aadu, 0x736a6d3bu};
+        return t[i];
+    }
 };
 // BLS12-377 scalar field (ark-bls12-377 0.5.0 Fr): 253 bits — the field of the reference's fft test.
 struct Fr377 {
@@ -60,6 +65,11 @@ struct Fr377 {
     __host__ __device__ static constexpr uint32_t r2(int i) {
         constexpr uint32_t t[8] = {0xb861857bu, 0x25d577bau, 0x8860591fu, 0xcc2c27b5u,
                                    0xe5dc8593u, 0xa7cc008fu, 0xeff1c939u, 0x011fdae7u};
+        return t[i];
+    }
+    __host__ __device__ static constexpr uint32_t k288(int i) {
+        constexpr uint32_t t[8] = {0x49adb84fu, 0x2f667ff2u, 0xef9e8ae2u, 0xe4a46e13u,
+                                   0xe7d8fb0eu, 0x29d63165u, 0xbdb3a756u, 0x00342799u};
         return t[i];
     }
 };
@@ -323,6 +333,72 @@ __device__ __forceinline__ Fe fe_mul_lazy(const Fe& a, const Fe& b) {
 template <class F>
 __device__ __forceinline__ Fe fe_mul(const Fe& a, const Fe& b) {
     return fe_reduce_once<F>(fe_mul_lazy<F>(a, b));
+}
+
+
+// ---- unreduced 512-bit product and deferred Montgomery reduction -------------------------------------
+// out[0..15] = a * b as a plain integer (no reduction): the same even/odd carry-chain rows as fe_mul_lazy
+// without the m*p half — 64 wide multiplies instead of 112.  Used for the LAST multiplication of each
+// sumcheck term: sum_j (x_j * y_j) is accumulated unreduced (17 words) and reduced once per thread.
+__device__ __forceinline__ void fe_mul_wide(uint32_t* out, const Fe& a, const Fe& b) {
+    uint32_t X[8], Y[8];
+    detail::mul4(Y, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
+    detail::mul4(X, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
+    out[0] = X[0];
+#pragma unroll
+    for (int i = 1; i < 8; i += 2) {
+        // odd row: even-column role = Y, odd-column role = X
+        detail::madc4_rshift(X, Y[0], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+        detail::cmad4(Y, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i], X[7]);
+        out[i] = Y[0];
+        if (i + 1 < 8) {
+            detail::madc4_rshift(Y, X[0], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
+            detail::cmad4(X, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1], Y[7]);
+            out[i + 1] = X[0];
+        }
+    }
+    // after row 7 the even-column array is Y (Y[0] emitted, Y[1..7] = columns 1..7), X = columns 1..8
+    asm("add.cc.u32 %0,%8,%16;\n\taddc.cc.u32 %1,%9,%17;\n\taddc.cc.u32 %2,%10,%18;\n\taddc.cc.u32 %3,%11,%19;\n\t"
+        "addc.cc.u32 %4,%12,%20;\n\taddc.cc.u32 %5,%13,%21;\n\taddc.cc.u32 %6,%14,%22;\n\taddc.u32 %7,%15,0;"
+        : "=r"(out[8]), "=r"(out[9]), "=r"(out[10]), "=r"(out[11]), "=r"(out[12]), "=r"(out[13]), "=r"(out[14]),
+          "=r"(out[15])
+        : "r"(X[0]), "r"(X[1]), "r"(X[2]), "r"(X[3]), "r"(X[4]), "r"(X[5]), "r"(X[6]), "r"(X[7]), "r"(Y[1]), "r"(Y[2]),
+          "r"(Y[3]), "r"(Y[4]), "r"(Y[5]), "r"(Y[6]), "r"(Y[7]));
+}
+
+// v[0..16] (a sum of < 2^22 such products, < 2^544) -> v * 2^-256 mod p, fully reduced.
+// Nine reduction rows divide by 2^288 (the result is then < p + 2^256-ish/2^32 < 2p), one multiplication by
+// 2^288 mod p restores the 2^-256 scaling of an ordinary Montgomery product.  Runs once per thread.
+template <class F>
+__device__ __noinline__ Fe fe_redc_wide(const uint32_t* vin) {
+    uint32_t v[18];
+#pragma unroll
+    for (int i = 0; i < 17; i++) v[i] = vin[i];
+    v[17] = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const uint32_t m = 0u - v[i];
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            c += (uint64_t)m * F::p(j) + v[i + j];
+            v[i + j] = (uint32_t)c;
+            c >>= 32;
+        }
+#pragma unroll
+        for (int j = i + 8; j < 18; j++) {
+            c += v[j];
+            v[j] = (uint32_t)c;
+            c >>= 32;
+        }
+    }
+    Fe u, k;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        u.v[i] = v[9 + i];
+        k.v[i] = F::k288(i);
+    }
+    return fe_mul<F>(fe_reduce_once<F>(u), k);
 }
 
 // Montgomery form <-> canonical integer (ark-ff `into_bigint` / `from_bigint`)

@@ -107,25 +107,68 @@ __device__ __forceinline__ void reduce_publish(Fe* acc, const ReduceArgs& ra) {
     }
 }
 
+// ---- wide (17-word) per-thread accumulators in shared memory -------------------------------------------
+// Layout: uint4 accw[t][5][kThreads]; words 0..15 = the unreduced sum, word 16 = overflow count.
+__device__ __forceinline__ void accw_zero(uint4* accw, int np) {
+    for (int i = threadIdx.x; i < np * 5 * kThreads; i += kThreads) accw[i] = make_uint4(0, 0, 0, 0);
+}
+// acc += w[0..15]  (one 17-word carry chain)
+__device__ __forceinline__ void accw_add16(uint4* a, const uint32_t* w) {
+    uint4 q0 = a[0 * kThreads], q1 = a[1 * kThreads], q2 = a[2 * kThreads], q3 = a[3 * kThreads], q4 = a[4 * kThreads];
+    asm("add.cc.u32 %0,%0,%17;\n\taddc.cc.u32 %1,%1,%18;\n\taddc.cc.u32 %2,%2,%19;\n\taddc.cc.u32 %3,%3,%20;\n\t"
+        "addc.cc.u32 %4,%4,%21;\n\taddc.cc.u32 %5,%5,%22;\n\taddc.cc.u32 %6,%6,%23;\n\taddc.cc.u32 %7,%7,%24;\n\t"
+        "addc.cc.u32 %8,%8,%25;\n\taddc.cc.u32 %9,%9,%26;\n\taddc.cc.u32 %10,%10,%27;\n\taddc.cc.u32 %11,%11,%28;\n\t"
+        "addc.cc.u32 %12,%12,%29;\n\taddc.cc.u32 %13,%13,%30;\n\taddc.cc.u32 %14,%14,%31;\n\taddc.cc.u32 %15,%15,%32;\n\t"
+        "addc.u32 %16,%16,0;"
+        : "+r"(q0.x), "+r"(q0.y), "+r"(q0.z), "+r"(q0.w), "+r"(q1.x), "+r"(q1.y), "+r"(q1.z), "+r"(q1.w), "+r"(q2.x),
+          "+r"(q2.y), "+r"(q2.z), "+r"(q2.w), "+r"(q3.x), "+r"(q3.y), "+r"(q3.z), "+r"(q3.w), "+r"(q4.x)
+        : "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]), "r"(w[9]),
+          "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]));
+    a[0 * kThreads] = q0; a[1 * kThreads] = q1; a[2 * kThreads] = q2; a[3 * kThreads] = q3; a[4 * kThreads] = q4;
+}
+// acc += x * 2^256 (x a reduced element): what an ordinary product x*R contributes before the deferred reduction
+__device__ __forceinline__ void accw_add_hi(uint4* a, const Fe& x) {
+    uint4 q2 = a[2 * kThreads], q3 = a[3 * kThreads], q4 = a[4 * kThreads];
+    asm("add.cc.u32 %0,%0,%9;\n\taddc.cc.u32 %1,%1,%10;\n\taddc.cc.u32 %2,%2,%11;\n\taddc.cc.u32 %3,%3,%12;\n\t"
+        "addc.cc.u32 %4,%4,%13;\n\taddc.cc.u32 %5,%5,%14;\n\taddc.cc.u32 %6,%6,%15;\n\taddc.cc.u32 %7,%7,%16;\n\t"
+        "addc.u32 %8,%8,0;"
+        : "+r"(q2.x), "+r"(q2.y), "+r"(q2.z), "+r"(q2.w), "+r"(q3.x), "+r"(q3.y), "+r"(q3.z), "+r"(q3.w), "+r"(q4.x)
+        : "r"(x.v[0]), "r"(x.v[1]), "r"(x.v[2]), "r"(x.v[3]), "r"(x.v[4]), "r"(x.v[5]), "r"(x.v[6]), "r"(x.v[7]));
+    a[2 * kThreads] = q2; a[3 * kThreads] = q3; a[4 * kThreads] = q4;
+}
+template <class F>
+__device__ __forceinline__ Fe accw_reduce(const uint4* a) {
+    uint32_t v[17];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint4 q = a[i * kThreads];
+        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+    }
+    v[16] = a[4 * kThreads].x;
+    return fe_redc_wide<F>(v);
+}
+
 // One hypercube item, all factors: lo_k / hi_k are the pair values of factor k for this item (after the
-// optional fold).  pr[t] = prod_k e_k(t), e_k(0) = lo_k, e_k(1) = hi_k, e_k(t+1) = e_k(t) + (hi_k - lo_k)
-// (prover.rs:49-56 evaluates at t = 0..D by a full partial_evaluate + prod_reduce each; the values are the
-// same field elements).  Factors are visited sequentially so that only the D+1 running products and one
-// factor's pair are live: registers stay low enough for 4-5 resident blocks per SM, which is what hides the
-// carry-chain latency of the multiplier, and the loop body (6 multiplications) stays inside the 32 KB
-// instruction cache.  `m` is a run-time value: one instantiation per degree serves every factor count.
+// optional fold).  Term t of the round polynomial is prod_k e_k(t), e_k(0) = lo_k, e_k(1) = hi_k,
+// e_k(t+1) = e_k(t) + (hi_k - lo_k)  (prover.rs:49-56 evaluates at t = 0..D by a full partial_evaluate +
+// prod_reduce each; the values are the same field elements).  Factors are visited sequentially so that only
+// the D+1 running products and one factor's pair are live (128 registers, 4 blocks per SM), and `m` is a
+// run-time value: one instantiation per degree serves every factor count.
+// The LAST multiplication of every term is not reduced: the 512-bit product is added to a 17-word
+// per-thread accumulator in shared memory and Montgomery-reduced once per thread at the end
+// (sum of products then one REDC == sum of REDCs, exactly, mod p): 64 instead of 112 wide multiplies.
 template <class F, int D, bool FOLD>
 __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
     round_kernel(TablePtrs tabs, int m, uint64_t q, Fe r_param, ReduceArgs ra) {
+    extern __shared__ uint4 accw_all[];  // [(D+1)][5][kThreads]
     __shared__ Fe* s_tab[kMaxFactors];
     if (threadIdx.x < kMaxFactors) s_tab[threadIdx.x] = tabs.t[threadIdx.x];
+    accw_zero(accw_all, D + 1);
     __syncthreads();
+    uint4* accw = accw_all + threadIdx.x;  // + t * 5 * kThreads + word_group * kThreads
     Fe r;  // the challenge, pinned into registers (a constant-bank multiplier operand defeats IMAD.WIDE fusion)
 #pragma unroll
     for (int i = 0; i < 8; i++) asm volatile("mov.u32 %0, %1;" : "=r"(r.v[i]) : "r"(r_param.v[i]));
-    Fe acc[D + 1];
-#pragma unroll
-    for (int t = 0; t <= D; t++) acc[t] = fe_zero<F>();
     const uint64_t stride = (uint64_t)gridDim.x * kThreads;
 #pragma unroll 1
     for (uint64_t j = (uint64_t)blockIdx.x * kThreads + threadIdx.x; j < q; j += stride) {
@@ -145,6 +188,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
                 lo = ld_fe_stream(T + j);
                 hi = ld_fe_stream(T + j + q);
             }
+            const bool last = (k == m - 1);
             if (k == 0) {
                 pr[0] = lo;
                 if (D >= 1) pr[1] = hi;
@@ -156,20 +200,29 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
                         pr[t] = hi;
                     }
                 }
+                if (last) {  // m == 1: the terms are the table values themselves
+#pragma unroll
+                    for (int t = 0; t <= D; t++) accw_add_hi(accw + t * 5 * kThreads, pr[t]);
+                }
             } else {
-                pr[0] = fe_mul<F>(lo, pr[0]);
+                uint32_t w[16];
+                if (last) { fe_mul_wide(w, lo, pr[0]); accw_add16(accw, w); } else pr[0] = fe_mul<F>(lo, pr[0]);
                 if (D >= 2) lo = fe_sub<F>(hi, lo);  // lo := d
-                if (D >= 1) pr[1] = fe_mul<F>(hi, pr[1]);
+                if (D >= 1) {
+                    if (last) { fe_mul_wide(w, hi, pr[1]); accw_add16(accw + 5 * kThreads, w); } else pr[1] = fe_mul<F>(hi, pr[1]);
+                }
 #pragma unroll
                 for (int t = 2; t <= D; t++) {
                     hi = fe_add<F>(hi, lo);
-                    pr[t] = fe_mul<F>(hi, pr[t]);
+                    if (last) { fe_mul_wide(w, hi, pr[t]); accw_add16(accw + t * 5 * kThreads, w); } else pr[t] = fe_mul<F>(hi, pr[t]);
                 }
             }
         }
-#pragma unroll
-        for (int t = 0; t <= D; t++) acc[t] = fe_add<F>(acc[t], pr[t]);
     }
+    Fe acc[D + 1];
+#pragma unroll 1
+    for (int t = 0; t <= D; t++) acc[t] = accw_reduce<F>(accw + t * 5 * kThreads);
+    __syncthreads();
     reduce_publish<F, D + 1>(acc, ra);
 }
 
@@ -240,9 +293,15 @@ Fe small_constant(unsigned t);  // Montgomery form of small integer t (host side
 
 template <class F, int D, bool FOLD>
 cudaError_t do_round(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st) {
-    static int bpsm = blocks_per_sm(round_kernel<F, D, FOLD>, kThreads);
+    constexpr size_t smem = (size_t)(D + 1) * 5 * kThreads * sizeof(uint4);
+    static int bpsm = [] {
+        cudaFuncSetAttribute(round_kernel<F, D, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<F, D, FOLD>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
+        return nb;
+    }();
     unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
-    round_kernel<F, D, FOLD><<<grid, kThreads, 0, st>>>(tabs, m, q, r, make_ra(s, 0));
+    round_kernel<F, D, FOLD><<<grid, kThreads, smem, st>>>(tabs, m, q, r, make_ra(s, 0));
     return cudaGetLastError();
 }
 template <class F, bool FOLD>
