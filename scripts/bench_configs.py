@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""All single-GPU BASELINE configs in one run (writes JSON lines to stdout):
+C1 n=20 m=1 D=1 prove+verify, C2 n=24 m=2 D=2 prove (absorb split out) + prove_partial, C3 n=26 m=3 D=3
+prove_partial, and the (m,D) shapes at n=24.  Times are medians of 5 after 2 warm-ups, CUDA events on the
+library stream around the C-ABI call (tables resident, regenerated in place between runs)."""
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import zk_b200 as zk
+from zk_b200 import _ffi
+
+lib = _ffi.lib()
+ctx = zk.Context(0)
+ext = torch.cuda.ExternalStream(ctx.stream_ptr())
+SEED = zk.DEFAULT_SEED
+
+
+def alg_muls(n, m, d):
+    return ((d + 1) * (m - 1) + m) * ((1 << n) - 1)
+
+
+def timed(fn, reps=5, warm=2, before=None):
+    ts = []
+    for i in range(warm + reps):
+        if before:
+            before()
+        ctx.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext); fn(); e1.record(ext); e1.synchronize()
+        if i >= warm:
+            ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts)
+
+
+def run(name, n, m, d, absorb, verify=False):
+    tabs = [zk.MultiLinearPolynomial.generate(n, k, seed=SEED, ctx=ctx) for k in range(m)]
+    claim = zk.ProductPoly(tabs).sum_mont()
+    rp = np.zeros((n, d + 1, 4), dtype=np.uint64); ch = np.zeros((n, 4), dtype=np.uint64); fin = np.zeros((m, 4), dtype=np.uint64)
+    arr = zk._table_array(tabs)
+
+    def regen():
+        for k in range(m):
+            tabs[k].regenerate(k, seed=SEED)
+
+    def prove():
+        ctx.check(lib.zk_sumcheck_prove(ctx.h, arr, m, d, claim.ctypes.data, int(absorb), rp.ctypes.data, ch.ctypes.data, fin.ctypes.data))
+
+    ms = timed(prove, before=regen)
+    pm = ctx.last_prove_ms()
+    out = {"config": name, "log_n": n, "m": m, "D": d, "absorb_initial_poly": absorb, "prove_ms": ms, "absorb_ms": pm["absorb_ms"],
+           "round_loop_ms": ms - pm["absorb_ms"], "kernel_ms": pm["kernel_ms"], "field_mul_per_s": alg_muls(n, m, d) / ((ms - pm["absorb_ms"]) * 1e-3),
+           "alg_gbs": 32 * m * ((1 << n) + 1.5 * ((1 << (n + 1)) - 2)) / ((ms - pm["absorb_ms"]) * 1e-3) / 1e9}
+    if verify:
+        regen()
+        st = {}
+
+        def ver():
+            st["rc"] = lib.zk_sumcheck_verify(ctx.h, arr, m, claim.ctypes.data, rp.ctypes.data, n, d)
+
+        out["verify_ms"] = timed(ver, reps=3, warm=1)
+        out["verify_ok"] = st["rc"] == 0
+    print(json.dumps(out), flush=True)
+
+
+run("C1 single MLE 2^20, prove+verify", 20, 1, 1, True, verify=True)
+run("C1 shape, prove_partial", 20, 1, 1, False)
+run("C2 product of 2 MLEs 2^24, prove (with absorb)", 24, 2, 2, True)
+run("C2 product of 2 MLEs 2^24, prove_partial", 24, 2, 2, False)
+run("(1,1) 2^24 prove_partial", 24, 1, 1, False)
+run("(3,3) 2^24 prove_partial", 24, 3, 3, False)
+run("(2,2) 2^26 prove_partial", 26, 2, 2, False)
+run("(1,1) 2^26 prove_partial", 26, 1, 1, False)
+run("C3 degree-3 product 2^26, prove_partial", 26, 3, 3, False)
+run("generic path (m=3, D=5) 2^22 prove_partial", 22, 3, 5, False)
