@@ -1,19 +1,14 @@
 // field29.cuh — carry-free Montgomery multiplication in a reduced radix (9 limbs x 29 bits, R' = 2^261).
 //
-// Why: on sm_100a an IMAD.WIDE.U32 that consumes or produces a carry predicate (IMAD.WIDE.U32.X) holds
-// the integer-multiply pipe ~4.3 cycles per warp instruction, a plain IMAD.WIDE.U32 only 2 (measured,
-// tools/ubench.cu: 29 vs 63 instr/clk/SM).  The radix-2^32 multiplier in field.cuh needs a carry on every
-// product; here limbs are 29 bits so a whole column of 29x29(+2 spare bits) products plus the reduction
-// products accumulates in ONE 64-bit register pair with no carries at all:
+// NEGATIVE RESULT, kept for the record (used only by tools/ubench.cu).  Hypothesis: IMAD.WIDE.U32 with carry
+// predicates is slower than a plain IMAD.WIDE.U32, so a radix-2^29 representation whose columns accumulate in one
+// 64-bit register pair without any carry should win.  Measured on B200: carries are free (29.7 vs 30.5 wide
+// multiplies per clock per SM) and the wide multiply itself is the half-rate, binding instruction; this form
+// needs 153-162 of them (9x9 + 9x8 + 9) against 112 for the radix-2^32 multiplier in field.cuh, and ptxas
+// additionally rewrites the accumulation into IMAD.WIDE(..,RZ) + 3-input IADD3 trees.  0.165 vs 0.25 mul/clk/SM.
+// It is bit-exact (mul29(a, 32*b) == fe_mul(a, b) on 2^20 random pairs, both fields).
 //     column k :  C += sum_{i+j=k} a_i b_j  +  sum_{i+j=k, j>0} m_i p_j ;   m_k = -C mod 2^29 ;  C = (C + m_k) >> 29
-// (product-scanning Montgomery, p == 1 mod 2^29 so the quotient digit is just a negation and p_0 = 1).
-// 162 IMAD.WIDE.U32 (2 cycles each) replace 97 IMAD.WIDE.U32.X + 31 others; the extra shifts/masks run on
-// the ALU pipe, which has slack.  Values in HBM keep the reference's layout (8x32-bit limbs, Montgomery
-// form with R = 2^256); conversion happens in registers at load/store.
-//
-// Scaling: mul29(x, y) = x*y*2^-261 mod p.  On Montgomery-form (R = 2^256) inputs aR, bR it returns
-// (ab)R * 2^-5, so callers fold a factor 2^5 per multiplication into a constant operand
-// (see kernels_sumcheck.cu); results written to memory are exact Montgomery-form values again.
+// Scaling: mul29(x, y) = x*y*2^-261 mod p.
 #pragma once
 #include "../zk_b200/csrc/field.cuh"
 
