@@ -56,9 +56,46 @@ struct ReduceArgs {
 };
 
 // Block-level reduction of NP per-thread accumulators, then grid-level via last-block-done.
-template <class F, int NP>
+// x / 2 in the field (works on any residue representation): (x + (x odd ? p : 0)) >> 1
+template <class F>
+__device__ __forceinline__ Fe fe_half(const Fe& x) {
+    const uint32_t mask = 0u - (x.v[0] & 1u);
+    uint32_t w[9];
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)x.v[i] + (F::p(i) & mask);
+        w[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    w[8] = (uint32_t)c;
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = (w[i] >> 1) | (w[i + 1] << 31);
+    return r;
+}
+// Toom evaluation set (0, 1, -1, inf) of a cubic -> the reference's evaluation set (0, 1, 2, 3).
+// v = {S(0), S(1), S(-1), c3}.  Exact field arithmetic, so the published values are the same field elements
+// the direct evaluation at t = 2, 3 produces.
+template <class F>
+__device__ __forceinline__ void toom_to_evals(Fe* v) {
+    const Fe s0 = v[0], s1 = v[1], sm = v[2], c3 = v[3];
+    const Fe c2 = fe_sub<F>(fe_half<F>(fe_add<F>(s1, sm)), s0);
+    const Fe c1 = fe_sub<F>(fe_half<F>(fe_sub<F>(s1, sm)), c3);
+    const Fe c1x2 = fe_add<F>(c1, c1), c2x2 = fe_add<F>(c2, c2), c2x4 = fe_add<F>(c2x2, c2x2), c2x8 = fe_add<F>(c2x4, c2x4);
+    const Fe c3x2 = fe_add<F>(c3, c3), c3x4 = fe_add<F>(c3x2, c3x2), c3x8 = fe_add<F>(c3x4, c3x4);
+    const Fe c3x16 = fe_add<F>(c3x8, c3x8), c3x32 = fe_add<F>(c3x16, c3x16);
+    // S(2) = s0 + 2 c1 + 4 c2 + 8 c3 ;  S(3) = s0 + 3 c1 + 9 c2 + 27 c3
+    v[2] = fe_add<F>(fe_add<F>(s0, c1x2), fe_add<F>(c2x4, c3x8));
+    const Fe c1x3 = fe_add<F>(c1x2, c1), c2x9 = fe_add<F>(c2x8, c2);
+    const Fe c3x27 = fe_sub<F>(fe_sub<F>(c3x32, c3x4), c3);
+    v[3] = fe_add<F>(fe_add<F>(s0, c1x3), fe_add<F>(c2x9, c3x27));
+}
+
+template <class F, int NP, bool TOOM = false>
 __device__ __forceinline__ void reduce_publish(Fe* acc, const ReduceArgs& ra) {
     __shared__ Fe sh[NP][kWarps];
+    __shared__ Fe s_fin[NP];
     __shared__ unsigned s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -95,13 +132,20 @@ __device__ __forceinline__ void reduce_publish(Fe* acc, const ReduceArgs& ra) {
         if (warp == 0) {
             Fe w = (lane < kWarps) ? sh[0][lane] : fe_zero<F>();
             w = warp_sum<F>(w, kWarps);
-            if (lane == 0) {
-                st_fe(ra.result_dev + ra.out_slot + t, w);
-                st_fe(ra.result_host + ra.out_slot + t, w);
-            }
+            if (lane == 0) s_fin[t] = w;
         }
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
+        Fe fin[NP];
+#pragma unroll
+        for (int t = 0; t < NP; t++) fin[t] = s_fin[t];
+        if (TOOM) toom_to_evals<F>(fin);
+#pragma unroll
+        for (int t = 0; t < NP; t++) {
+            st_fe(ra.result_dev + ra.out_slot + t, fin[t]);
+            st_fe(ra.result_host + ra.out_slot + t, fin[t]);
+        }
         *ra.ticket = 0;  // ready for the next launch on this stream
         __threadfence_system();
     }
@@ -157,9 +201,14 @@ __device__ __forceinline__ Fe accw_reduce(const uint4* a) {
 // The LAST multiplication of every term is not reduced: the 512-bit product is added to a 17-word
 // per-thread accumulator in shared memory and Montgomery-reduced once per thread at the end
 // (sum of products then one REDC == sum of REDCs, exactly, mod p): 64 instead of 112 wide multiplies.
-template <class F, int D, bool FOLD>
+// TOOM (only D == 3 with exactly three factors): the terms are carried at the points (0, 1, -1, inf)
+// instead of (0, 1, 2, 3).  After the second factor the running product is a quadratic, fixed by three
+// values, so its value at -1 is 2(A(0) + A(inf)) - A(1): one multiplication less per item (7 instead of 8).
+// The four sums are mapped back to S(0..3) by exact field arithmetic in the last block (toom_to_evals).
+template <class F, int D, bool FOLD, bool TOOM = false>
 __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
     round_kernel(TablePtrs tabs, int m, uint64_t q, Fe r_param, ReduceArgs ra) {
+    static_assert(!TOOM || D == 3, "the Toom point set is wired for cubics");
     extern __shared__ uint4 accw_all[];  // [(D+1)][5][kThreads]
     __shared__ Fe* s_tab[kMaxFactors];
     if (threadIdx.x < kMaxFactors) s_tab[threadIdx.x] = tabs.t[threadIdx.x];
@@ -189,7 +238,24 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
                 hi = ld_fe_stream(T + j + q);
             }
             const bool last = (k == m - 1);
-            if (k == 0) {
+            if (TOOM) {  // pr[0..3] live at t = 0, 1, -1, inf ; m == 3
+                const Fe d = fe_sub<F>(hi, lo);
+                if (k == 0) {
+                    pr[0] = lo; pr[1] = hi; pr[3] = d; pr[2] = fe_sub<F>(lo, d);
+                } else if (!last) {
+                    pr[0] = fe_mul<F>(lo, pr[0]);
+                    pr[1] = fe_mul<F>(hi, pr[1]);
+                    pr[3] = fe_mul<F>(d, pr[3]);
+                    const Fe s02 = fe_add<F>(pr[0], pr[3]);
+                    pr[2] = fe_sub<F>(fe_add<F>(s02, s02), pr[1]);
+                } else {
+                    uint32_t w[16];
+                    fe_mul_wide(w, lo, pr[0]); accw_add16(accw, w);
+                    fe_mul_wide(w, hi, pr[1]); accw_add16(accw + 5 * kThreads, w);
+                    fe_mul_wide(w, fe_sub<F>(lo, d), pr[2]); accw_add16(accw + 2 * 5 * kThreads, w);
+                    fe_mul_wide(w, d, pr[3]); accw_add16(accw + 3 * 5 * kThreads, w);
+                }
+            } else if (k == 0) {
                 pr[0] = lo;
                 if (D >= 1) pr[1] = hi;
                 if (D >= 2) {
@@ -223,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
 #pragma unroll 1
     for (int t = 0; t <= D; t++) acc[t] = accw_reduce<F>(accw + t * 5 * kThreads);
     __syncthreads();
-    reduce_publish<F, D + 1>(acc, ra);
+    reduce_publish<F, D + 1, TOOM>(acc, ra);
 }
 
 // grid.y = factor index
@@ -291,17 +357,17 @@ inline ReduceArgs make_ra(const ReduceScratch& s, int slot) {
 template <class F>
 Fe small_constant(unsigned t);  // Montgomery form of small integer t (host side)
 
-template <class F, int D, bool FOLD>
+template <class F, int D, bool FOLD, bool TOOM = false>
 cudaError_t do_round(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st) {
     constexpr size_t smem = (size_t)(D + 1) * 5 * kThreads * sizeof(uint4);
     static int bpsm = [] {
-        cudaFuncSetAttribute(round_kernel<F, D, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(round_kernel<F, D, FOLD, TOOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<F, D, FOLD>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<F, D, FOLD, TOOM>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
         return nb;
     }();
     unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
-    round_kernel<F, D, FOLD><<<grid, kThreads, smem, st>>>(tabs, m, q, r, make_ra(s, 0));
+    round_kernel<F, D, FOLD, TOOM><<<grid, kThreads, smem, st>>>(tabs, m, q, r, make_ra(s, 0));
     return cudaGetLastError();
 }
 template <class F, bool FOLD>
@@ -310,7 +376,7 @@ cudaError_t do_round_deg(const TablePtrs& tabs, int m, int degree, uint64_t q, c
     switch (degree) {
         case 1: return do_round<F, 1, FOLD>(tabs, m, q, r, s, st);
         case 2: return do_round<F, 2, FOLD>(tabs, m, q, r, s, st);
-        case 3: return do_round<F, 3, FOLD>(tabs, m, q, r, s, st);
+        case 3: return m == 3 ? do_round<F, 3, FOLD, true>(tabs, m, q, r, s, st) : do_round<F, 3, FOLD>(tabs, m, q, r, s, st);
         case 4: return do_round<F, 4, FOLD>(tabs, m, q, r, s, st);
         default: return cudaErrorInvalidValue;
     }
