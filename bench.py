@@ -120,6 +120,9 @@ def run_reference(args):
     m, d = args.m, args.degree
     n_full = args.log_n if args.log_n else 26 + (args.gpus.bit_length() - 1)
     n = args.cpu_log_n
+    # bounded sample: keep the whole --steps/--warmup run within a few minutes (~5-11 s per 2^22 proof on one core)
+    while n > 16 and (args.steps + min(args.warmup, 1)) * 11.0 * (1 << n) / (1 << 22) > 240.0:
+        n -= 1
     times = cpu_reference_run(n, m, d, args.steps, min(args.warmup, 1))
     sec = sum(times) / len(times)
     value = alg_muls(n, m, d) / sec

@@ -26,8 +26,9 @@ def alg_muls(n, m, d):
     return ((d + 1) * (m - 1) + m) * ((1 << n) - 1)
 
 
-def timed(fn, reps=5, warm=2, before=None):
-    ts = []
+def timed(fn, reps=5, warm=2, before=None, after=None):
+    """median run: returns (ms, after() of that same run)"""
+    runs = []
     for i in range(warm + reps):
         if before:
             before()
@@ -35,8 +36,9 @@ def timed(fn, reps=5, warm=2, before=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(ext); fn(); e1.record(ext); e1.synchronize()
         if i >= warm:
-            ts.append(e0.elapsed_time(e1))
-    return statistics.median(ts)
+            runs.append((e0.elapsed_time(e1), after() if after else None))
+    runs.sort(key=lambda x: x[0])
+    return runs[len(runs) // 2]
 
 
 def run(name, n, m, d, absorb, verify=False):
@@ -52,8 +54,7 @@ def run(name, n, m, d, absorb, verify=False):
     def prove():
         ctx.check(lib.zk_sumcheck_prove(ctx.h, arr, m, d, claim.ctypes.data, int(absorb), rp.ctypes.data, ch.ctypes.data, fin.ctypes.data))
 
-    ms = timed(prove, before=regen)
-    pm = ctx.last_prove_ms()
+    ms, pm = timed(prove, before=regen, after=ctx.last_prove_ms)
     out = {"config": name, "log_n": n, "m": m, "D": d, "absorb_initial_poly": absorb, "prove_ms": ms, "absorb_ms": pm["absorb_ms"],
            "round_loop_ms": ms - pm["absorb_ms"], "kernel_ms": pm["kernel_ms"], "field_mul_per_s": alg_muls(n, m, d) / ((ms - pm["absorb_ms"]) * 1e-3),
            "alg_gbs": 32 * m * ((1 << n) + 1.5 * ((1 << (n + 1)) - 2)) / ((ms - pm["absorb_ms"]) * 1e-3) / 1e9}
@@ -64,7 +65,7 @@ def run(name, n, m, d, absorb, verify=False):
         def ver():
             st["rc"] = lib.zk_sumcheck_verify(ctx.h, arr, m, claim.ctypes.data, rp.ctypes.data, n, d)
 
-        out["verify_ms"] = timed(ver, reps=3, warm=1)
+        out["verify_ms"] = timed(ver, reps=3, warm=1)[0]
         out["verify_ok"] = st["rc"] == 0
     print(json.dumps(out), flush=True)
 

@@ -31,6 +31,21 @@ def test_to_bytes(zk, ctx, cref, fid):
     assert t.to_bytes() == cref.to_bytes(fid, cref.gen_table(fid, 5, 1, 9))
 
 
+def test_regenerate_in_place(zk, ctx, cref):
+    t = zk.MultiLinearPolynomial.generate(10, 0, seed=1)
+    t.regenerate(2, seed=77)
+    assert (t.evaluation_slice_mont() == cref.gen_table(0, 77, 2, 10)).all()
+    # a table consumed by prove can be refilled and proved again with the same result
+    tabs = [zk.MultiLinearPolynomial.generate(11, k, seed=9) for k in range(3)]
+    pp = zk.ProductPoly.new(tabs)
+    claim = pp.sum()
+    p1, c1 = zk.SumcheckProver(3).prove_partial(pp, claim)
+    for k in range(3):
+        tabs[k].regenerate(k, seed=9)
+    p2, c2 = zk.SumcheckProver(3).prove_partial(pp, claim)
+    assert p1.round_polys == p2.round_polys and c1 == c2
+
+
 def test_upload_download_roundtrip(zk, ctx, cref):
     ref = cref.gen_table(0, 123, 0, 12)
     t = zk.MultiLinearPolynomial.new(12, ref)

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -127,6 +128,10 @@ int cuda_fail(zk_ctx* ctx, cudaError_t e, const char* where) {
         if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
     } while (0)
 
+// every reducing launch publishes a fresh non-zero sequence number to the mapped completion flag
+inline void next_seq(zk_ctx* ctx) {
+    if (++ctx->scratch.seq == 0) ctx->scratch.seq = 1;
+}
 inline void count(zk_ctx* ctx) {
     ctx->launches_total += (uint64_t)ctx->launches;
     ctx->launches = 0;
@@ -190,7 +195,26 @@ int finish_reduction(zk_ctx* ctx, int field, int count_elems, uint64_t* out, boo
         CU(ctx, zk::launch_narrow(field, ctx->lanes, ctx->scratch.result_dev, ctx->scratch.result_host_devptr, count_elems,
                                   ctx->stream, &ctx->launches));
     }
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (allreduce && ctx->world > 1) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        // spin on the mapped completion flag the last block stores after the results (a few microseconds
+        // cheaper per round than a stream synchronisation); fall back to the stream status every so often so
+        // that a failed launch cannot hang the caller
+        volatile unsigned* flag = ctx->scratch.flag_host;
+        const unsigned want = ctx->scratch.seq;
+        for (unsigned spins = 0; *flag != want; spins++) {
+            if ((spins & 0x3fff) == 0x3fff) {
+                cudaError_t q = cudaStreamQuery(ctx->stream);
+                if (q == cudaSuccess) {
+                    if (*flag != want) CU(ctx, cudaStreamSynchronize(ctx->stream));
+                    break;
+                }
+                if (q != cudaErrorNotReady) return cuda_fail(ctx, q, "round kernel");
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    }
     if (out) std::memcpy(out, ctx->scratch.result_host, (size_t)count_elems * 32);
     return ZK_OK;
 }
@@ -208,6 +232,10 @@ int ctx_init(zk_ctx* c) {
     CU(c, cudaMalloc((void**)&c->scratch.result_dev, (zk::kMaxDegree + 1) * sizeof(Fe)));
     CU(c, cudaHostAlloc((void**)&c->scratch.result_host, (zk::kMaxDegree + 1) * sizeof(Fe), cudaHostAllocMapped));
     CU(c, cudaHostGetDevicePointer((void**)&c->scratch.result_host_devptr, c->scratch.result_host, 0));
+    CU(c, cudaHostAlloc((void**)&c->scratch.flag_host, 64, cudaHostAllocMapped));
+    *c->scratch.flag_host = 0;
+    CU(c, cudaHostGetDevicePointer((void**)&c->scratch.flag_host_devptr, c->scratch.flag_host, 0));
+    c->scratch.seq = 0;
     CU(c, cudaMalloc((void**)&c->lanes, (zk::kMaxDegree + 1) * 8 * sizeof(uint64_t)));
     c->events.resize(2 * 260);
     for (auto& ev : c->events) CU(c, cudaEventCreate(&ev));
@@ -292,6 +320,7 @@ void zk_ctx_destroy(zk_ctx* c) {
     cudaFree(c->scratch.ticket);
     cudaFree(c->scratch.result_dev);
     cudaFreeHost(c->scratch.result_host);
+    cudaFreeHost(c->scratch.flag_host);
     cudaFree(c->lanes);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -557,6 +586,7 @@ int zk_product_sum(zk_ctx* ctx, const zk_table* const* tables, unsigned m, uint6
     int st = product_check(ctx, tables, m, true);
     if (st != ZK_OK) return st;
     CU(ctx, cudaSetDevice(ctx->device));
+    next_seq(ctx);
     CU(ctx, zk::launch_product_sum(tables[0]->field, ptrs_of(tables, m), (int)m, tables[0]->local_len, ctx->scratch,
                                    ctx->stream, &ctx->launches));
     st = finish_reduction(ctx, tables[0]->field, 1, out, true);
@@ -571,6 +601,7 @@ int zk_product_round_poly(zk_ctx* ctx, const zk_table* const* tables, unsigned m
     if (degree > ZK_MAX_DEGREE) return fail(ctx, ZK_ERR_UNSUPPORTED, "degree > ZK_MAX_DEGREE");
     if (tables[0]->n_vars == 0 || tables[0]->local_len < 2) return fail(ctx, ZK_ERR_VAR_RANGE);
     CU(ctx, cudaSetDevice(ctx->device));
+    next_seq(ctx);
     CU(ctx, zk::launch_round_poly(tables[0]->field, ptrs_of(tables, m), (int)m, (int)degree, tables[0]->local_len / 2,
                                   ctx->scratch, ctx->stream, &ctx->launches));
     st = finish_reduction(ctx, tables[0]->field, (int)degree + 1, out, true);
@@ -603,6 +634,7 @@ int zk_product_fold_then_round_poly(zk_ctx* ctx, zk_table* const* tables, unsign
     if (degree > ZK_MAX_DEGREE) return fail(ctx, ZK_ERR_UNSUPPORTED, "degree > ZK_MAX_DEGREE");
     if (tables[0]->n_vars < 2 || tables[0]->local_len < 4) return fail(ctx, ZK_ERR_VAR_RANGE);
     CU(ctx, cudaSetDevice(ctx->device));
+    next_seq(ctx);
     CU(ctx, zk::launch_fold_round_poly(tables[0]->field, ptrs_of(tables, m), (int)m, (int)degree, tables[0]->local_len,
                                        fe_from_u64x4(r), ctx->scratch, ctx->stream, &ctx->launches));
     st = finish_reduction(ctx, tables[0]->field, (int)degree + 1, out, true);
@@ -749,7 +781,7 @@ int zk_sumcheck_prove(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
             st = gather();
             if (st != ZK_OK) { cleanup(); return st; }
         }
-        cudaError_t e = timed([&] { return zk::launch_round_poly(field, cur, (int)m, (int)degree, cur_len / 2, ctx->scratch, ctx->stream, &ctx->launches); });
+        cudaError_t e = timed([&] { next_seq(ctx); return zk::launch_round_poly(field, cur, (int)m, (int)degree, cur_len / 2, ctx->scratch, ctx->stream, &ctx->launches); });
         if (e != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "round_poly"); }
         if (perf_log_enabled()) {
             cudaStreamSynchronize(ctx->stream);
@@ -785,9 +817,9 @@ int zk_sumcheck_prove(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
             if (e != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "fold"); }
             st = gather();
             if (st != ZK_OK) { cleanup(); return st; }
-            e = timed([&] { return zk::launch_round_poly(field, cur, (int)m, (int)degree, cur_len / 2, ctx->scratch, ctx->stream, &ctx->launches); });
+            e = timed([&] { next_seq(ctx); return zk::launch_round_poly(field, cur, (int)m, (int)degree, cur_len / 2, ctx->scratch, ctx->stream, &ctx->launches); });
         } else {
-            e = timed([&] { return zk::launch_fold_round_poly(field, cur, (int)m, (int)degree, cur_len, rf, ctx->scratch, ctx->stream, &ctx->launches); });
+            e = timed([&] { next_seq(ctx); return zk::launch_fold_round_poly(field, cur, (int)m, (int)degree, cur_len, rf, ctx->scratch, ctx->stream, &ctx->launches); });
             cur_len /= 2;
         }
         if (e != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "fold_round_poly"); }

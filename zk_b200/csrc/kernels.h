@@ -25,6 +25,9 @@ struct ReduceScratch {
     Fe* result_dev;          // [(kMaxDegree+1)] device copy of the last result
     Fe* result_host;         // [(kMaxDegree+1)] pinned+mapped host memory (device-visible alias below)
     Fe* result_host_devptr;  // device pointer aliasing result_host
+    unsigned* flag_host;     // pinned+mapped completion flag: the last block stores `seq` after the results
+    unsigned* flag_host_devptr;
+    unsigned seq;            // value the next reducing launch publishes (0 = do not publish)
     int num_sms;
 };
 

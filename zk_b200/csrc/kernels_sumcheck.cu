@@ -22,6 +22,7 @@ namespace zk {
 namespace {
 
 constexpr int kThreads = 128;
+
 constexpr int kWarps = kThreads / 32;
 
 __device__ __forceinline__ Fe ld_fe_cg(const Fe* p) {  // L2-coherent load (other blocks' partials)
@@ -53,6 +54,8 @@ struct ReduceArgs {
     Fe* result_dev;
     Fe* result_host;
     int out_slot;
+    unsigned* flag_host;  // mapped pinned word the host spins on (saves a stream synchronisation per round)
+    unsigned seq;
 };
 
 // Block-level reduction of NP per-thread accumulators, then grid-level via last-block-done.
@@ -148,6 +151,10 @@ __device__ __forceinline__ void reduce_publish(Fe* acc, const ReduceArgs& ra) {
         }
         *ra.ticket = 0;  // ready for the next launch on this stream
         __threadfence_system();
+        if (ra.seq != 0) {
+            *(volatile unsigned*)ra.flag_host = ra.seq;
+            __threadfence_system();
+        }
     }
 }
 
@@ -219,8 +226,18 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
 #pragma unroll
     for (int i = 0; i < 8; i++) asm volatile("mov.u32 %0, %1;" : "=r"(r.v[i]) : "r"(r_param.v[i]));
     const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+    const uint64_t j0 = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    // Round 0 (no fold) software-pipelines its loads: the pair of the next (item, factor) is in flight while this
+    // one is multiplied (+6 % on that kernel).  The fused kernel does not: the four extra elements cost 32
+    // registers and measured slower.
+    constexpr bool kPrefetch = !FOLD;
+    Fe n0, n1;
+    if (kPrefetch && j0 < q) {
+        n0 = ld_fe_stream(s_tab[0] + j0);
+        n1 = ld_fe_stream(s_tab[0] + j0 + q);
+    }
 #pragma unroll 1
-    for (uint64_t j = (uint64_t)blockIdx.x * kThreads + threadIdx.x; j < q; j += stride) {
+    for (uint64_t j = j0; j < q; j += stride) {
         Fe pr[D + 1];
 #pragma unroll 1
         for (int k = 0; k < m; k++) {
@@ -234,8 +251,15 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
                 hi = fe_fold<F>(x1, x3, r);
                 st_fe(T + j + q, hi);
             } else {  // T has 2q entries: the pair is (j, j+q)
-                lo = ld_fe_stream(T + j);
-                hi = ld_fe_stream(T + j + q);
+                lo = n0;
+                hi = n1;
+                const bool more_k = (k + 1 < m);
+                const uint64_t nj = more_k ? j : j + stride;
+                if (nj < q) {
+                    Fe* NT = s_tab[more_k ? k + 1 : 0];
+                    n0 = ld_fe_stream(NT + nj);
+                    n1 = ld_fe_stream(NT + nj + q);
+                }
             }
             const bool last = (k == m - 1);
             if (TOOM) {  // pr[0..3] live at t = 0, 1, -1, inf ; m == 3
@@ -352,7 +376,7 @@ inline unsigned grid_for(uint64_t items, int threads, int num_sms, int bpsm) {
     return (unsigned)(need < cap ? need : cap);
 }
 inline ReduceArgs make_ra(const ReduceScratch& s, int slot) {
-    return ReduceArgs{s.block_partials, s.ticket, s.result_dev, s.result_host_devptr, slot};
+    return ReduceArgs{s.block_partials, s.ticket, s.result_dev, s.result_host_devptr, slot, s.flag_host_devptr, s.seq};
 }
 template <class F>
 Fe small_constant(unsigned t);  // Montgomery form of small integer t (host side)
@@ -407,7 +431,9 @@ cudaError_t round_poly_dispatch(const TablePtrs& tabs, int m, int degree, uint64
     static int bpsm = blocks_per_sm(eval_at_kernel<F>, kThreads);
     unsigned grid = grid_for(half, kThreads, s.num_sms, bpsm);
     for (int t = 0; t <= degree; t++) {
-        eval_at_kernel<F><<<grid, kThreads, 0, st>>>(tabs, m, half, host_small_mont<F>((unsigned)t), make_ra(s, t));
+        ReduceArgs ra = make_ra(s, t);
+        if (t != degree) ra.seq = 0;  // only the last launch of the group publishes the completion flag
+        eval_at_kernel<F><<<grid, kThreads, 0, st>>>(tabs, m, half, host_small_mont<F>((unsigned)t), ra);
         ++*launches;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
