@@ -74,6 +74,9 @@ struct zk_ctx {
     std::vector<float> round_ms;
     double prove_ms[3] = {0, 0, 0};
     std::vector<zk::NttPlan*> ntt_plans;  // small cache: twiddle tables are reused across calls
+    unsigned cur_seq = 0;                 // sequence number of the reduction in flight
+    Fe* gather_buf = nullptr;             // persistent staging for the residual all-gather (grow-only)
+    size_t gather_cap = 0;                // elements
 };
 
 struct zk_table {
@@ -129,8 +132,13 @@ int cuda_fail(zk_ctx* ctx, cudaError_t e, const char* where) {
     } while (0)
 
 // every reducing launch publishes a fresh non-zero sequence number to the mapped completion flag
-inline void next_seq(zk_ctx* ctx) {
-    if (++ctx->scratch.seq == 0) ctx->scratch.seq = 1;
+// `will_allreduce`: the launch's result is a per-rank partial — it widens it into the all-reduce lanes and
+// leaves the flag alone; the narrowing kernel after the all-reduce publishes the sequence number instead.
+inline void next_seq(zk_ctx* ctx, bool will_allreduce = false) {
+    if (++ctx->cur_seq == 0) ctx->cur_seq = 1;
+    const bool sharded = will_allreduce && ctx->world > 1;
+    ctx->scratch.seq = sharded ? 0u : ctx->cur_seq;
+    ctx->scratch.lanes = sharded ? ctx->lanes : nullptr;
 }
 inline void count(zk_ctx* ctx) {
     ctx->launches_total += (uint64_t)ctx->launches;
@@ -188,33 +196,29 @@ zk::TablePtrs ptrs_of(const zk_table* const* tables, unsigned m) {
 // result in pinned host memory and copy it out.
 int finish_reduction(zk_ctx* ctx, int field, int count_elems, uint64_t* out, bool allreduce) {
     if (allreduce && ctx->world > 1) {
-        CU(ctx, zk::launch_widen(ctx->scratch.result_dev, ctx->lanes, count_elems, ctx->stream, &ctx->launches));
+        // the reducing launch already wrote one 32-bit limb per u64 lane (ReduceScratch::lanes)
         int rc = nccl().AllReduce(ctx->lanes, ctx->lanes, (size_t)count_elems * 8, kNcclUint64, kNcclSum, ctx->comm,
                                   ctx->stream);
         if (rc != 0) return fail(ctx, ZK_ERR_NCCL, nccl().GetErrorString ? nccl().GetErrorString(rc) : "allreduce");
         CU(ctx, zk::launch_narrow(field, ctx->lanes, ctx->scratch.result_dev, ctx->scratch.result_host_devptr, count_elems,
-                                  ctx->stream, &ctx->launches));
+                                  ctx->scratch.flag_host_devptr, ctx->cur_seq, ctx->stream, &ctx->launches));
     }
-    if (allreduce && ctx->world > 1) {
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
-    } else {
-        // spin on the mapped completion flag the last block stores after the results (a few microseconds
-        // cheaper per round than a stream synchronisation); fall back to the stream status every so often so
-        // that a failed launch cannot hang the caller
-        volatile unsigned* flag = ctx->scratch.flag_host;
-        const unsigned want = ctx->scratch.seq;
-        for (unsigned spins = 0; *flag != want; spins++) {
-            if ((spins & 0x3fff) == 0x3fff) {
-                cudaError_t q = cudaStreamQuery(ctx->stream);
-                if (q == cudaSuccess) {
-                    if (*flag != want) CU(ctx, cudaStreamSynchronize(ctx->stream));
-                    break;
-                }
-                if (q != cudaErrorNotReady) return cuda_fail(ctx, q, "round kernel");
+    // spin on the mapped completion flag the last block (or the narrowing kernel) stores after the results: a few
+    // microseconds cheaper per round than a stream synchronisation; the stream status is consulted every so
+    // often so that a failed launch cannot hang the caller
+    volatile unsigned* flag = ctx->scratch.flag_host;
+    const unsigned want = ctx->cur_seq;
+    for (unsigned spins = 0; *flag != want; spins++) {
+        if ((spins & 0x3fff) == 0x3fff) {
+            cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q == cudaSuccess) {
+                if (*flag != want) CU(ctx, cudaStreamSynchronize(ctx->stream));
+                break;
             }
+            if (q != cudaErrorNotReady) return cuda_fail(ctx, q, "round kernel");
         }
-        std::atomic_thread_fence(std::memory_order_acquire);
     }
+    std::atomic_thread_fence(std::memory_order_acquire);
     if (out) std::memcpy(out, ctx->scratch.result_host, (size_t)count_elems * 32);
     return ZK_OK;
 }
@@ -315,6 +319,7 @@ void zk_ctx_destroy(zk_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm) nccl().CommDestroy(c->comm);
     for (auto* pl : c->ntt_plans) zk::ntt_plan_destroy(pl);
+    cudaFree(c->gather_buf);
     for (auto ev : c->events) cudaEventDestroy(ev);
     cudaFree(c->scratch.block_partials);
     cudaFree(c->scratch.ticket);
@@ -586,7 +591,7 @@ int zk_product_sum(zk_ctx* ctx, const zk_table* const* tables, unsigned m, uint6
     int st = product_check(ctx, tables, m, true);
     if (st != ZK_OK) return st;
     CU(ctx, cudaSetDevice(ctx->device));
-    next_seq(ctx);
+    next_seq(ctx, true);
     CU(ctx, zk::launch_product_sum(tables[0]->field, ptrs_of(tables, m), (int)m, tables[0]->local_len, ctx->scratch,
                                    ctx->stream, &ctx->launches));
     st = finish_reduction(ctx, tables[0]->field, 1, out, true);
@@ -601,7 +606,7 @@ int zk_product_round_poly(zk_ctx* ctx, const zk_table* const* tables, unsigned m
     if (degree > ZK_MAX_DEGREE) return fail(ctx, ZK_ERR_UNSUPPORTED, "degree > ZK_MAX_DEGREE");
     if (tables[0]->n_vars == 0 || tables[0]->local_len < 2) return fail(ctx, ZK_ERR_VAR_RANGE);
     CU(ctx, cudaSetDevice(ctx->device));
-    next_seq(ctx);
+    next_seq(ctx, true);
     CU(ctx, zk::launch_round_poly(tables[0]->field, ptrs_of(tables, m), (int)m, (int)degree, tables[0]->local_len / 2,
                                   ctx->scratch, ctx->stream, &ctx->launches));
     st = finish_reduction(ctx, tables[0]->field, (int)degree + 1, out, true);
@@ -634,7 +639,7 @@ int zk_product_fold_then_round_poly(zk_ctx* ctx, zk_table* const* tables, unsign
     if (degree > ZK_MAX_DEGREE) return fail(ctx, ZK_ERR_UNSUPPORTED, "degree > ZK_MAX_DEGREE");
     if (tables[0]->n_vars < 2 || tables[0]->local_len < 4) return fail(ctx, ZK_ERR_VAR_RANGE);
     CU(ctx, cudaSetDevice(ctx->device));
-    next_seq(ctx);
+    next_seq(ctx, true);
     CU(ctx, zk::launch_fold_round_poly(tables[0]->field, ptrs_of(tables, m), (int)m, (int)degree, tables[0]->local_len,
                                        fe_from_u64x4(r), ctx->scratch, ctx->stream, &ctx->launches));
     st = finish_reduction(ctx, tables[0]->field, (int)degree + 1, out, true);
@@ -741,24 +746,28 @@ int zk_sumcheck_prove(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
     zk::TablePtrs cur = ptrs_of(tables, m);
     uint64_t cur_len = tables[0]->local_len;
     bool sharded = ctx->world > 1;
-    std::vector<Fe*> gathered;  // owned buffers after the residual gather
-    auto cleanup = [&]() { for (Fe* p : gathered) cudaFreeAsync(p, ctx->stream); };
+    auto cleanup = [&]() {};
 
     // Gather the per-rank residual tables (local length L) into full tables of L*world entries on every rank.
     auto gather = [&]() -> int {
         const uint64_t L = cur_len, G = (uint64_t)ctx->world;
+        // persistent staging (grow-only): [m] all-gather landing zones + [m] interleaved tables
+        const size_t need = (size_t)(2 * m * L * G);
+        if (ctx->gather_cap < need) {
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->gather_buf);
+            ctx->gather_buf = nullptr;
+            ctx->gather_cap = 0;
+            CU(ctx, cudaMalloc((void**)&ctx->gather_buf, need * sizeof(Fe)));
+            ctx->gather_cap = need;
+        }
         for (unsigned k = 0; k < m; k++) {
-            // stream-ordered allocations: no device-wide synchronisation on the critical path
-            Fe *stage = nullptr, *full = nullptr;
-            cudaError_t e = cudaMallocAsync((void**)&stage, (size_t)(L * G) * 32, ctx->stream);
-            if (e == cudaSuccess) e = cudaMallocAsync((void**)&full, (size_t)(L * G) * 32, ctx->stream);
-            if (e != cudaSuccess) { if (stage) cudaFreeAsync(stage, ctx->stream); return cuda_fail(ctx, e, "gather alloc"); }
+            Fe* stage = ctx->gather_buf + (size_t)k * L * G;
+            Fe* full = ctx->gather_buf + (size_t)(m + k) * L * G;
             int rc = nccl().AllGather(cur.t[k], stage, (size_t)L * 32, kNcclUint8, ctx->comm, ctx->stream);
-            if (rc != 0) { cudaFreeAsync(stage, ctx->stream); cudaFreeAsync(full, ctx->stream); return fail(ctx, ZK_ERR_NCCL, "allgather"); }
-            e = zk::launch_interleave(stage, full, L, (unsigned)G, ctx->stream, &ctx->launches);
-            cudaFreeAsync(stage, ctx->stream);
-            if (e != cudaSuccess) { cudaFreeAsync(full, ctx->stream); return cuda_fail(ctx, e, "gather"); }
-            gathered.push_back(full);
+            if (rc != 0) return fail(ctx, ZK_ERR_NCCL, "allgather");
+            cudaError_t e = zk::launch_interleave(stage, full, L, (unsigned)G, ctx->stream, &ctx->launches);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "gather");
             cur.t[k] = full;
         }
         cur_len = L * G;
@@ -781,7 +790,7 @@ int zk_sumcheck_prove(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
             st = gather();
             if (st != ZK_OK) { cleanup(); return st; }
         }
-        cudaError_t e = timed([&] { next_seq(ctx); return zk::launch_round_poly(field, cur, (int)m, (int)degree, cur_len / 2, ctx->scratch, ctx->stream, &ctx->launches); });
+        cudaError_t e = timed([&] { next_seq(ctx, sharded); return zk::launch_round_poly(field, cur, (int)m, (int)degree, cur_len / 2, ctx->scratch, ctx->stream, &ctx->launches); });
         if (e != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "round_poly"); }
         if (perf_log_enabled()) {
             cudaStreamSynchronize(ctx->stream);
@@ -817,9 +826,9 @@ int zk_sumcheck_prove(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
             if (e != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "fold"); }
             st = gather();
             if (st != ZK_OK) { cleanup(); return st; }
-            e = timed([&] { next_seq(ctx); return zk::launch_round_poly(field, cur, (int)m, (int)degree, cur_len / 2, ctx->scratch, ctx->stream, &ctx->launches); });
+            e = timed([&] { next_seq(ctx, sharded); return zk::launch_round_poly(field, cur, (int)m, (int)degree, cur_len / 2, ctx->scratch, ctx->stream, &ctx->launches); });
         } else {
-            e = timed([&] { next_seq(ctx); return zk::launch_fold_round_poly(field, cur, (int)m, (int)degree, cur_len, rf, ctx->scratch, ctx->stream, &ctx->launches); });
+            e = timed([&] { next_seq(ctx, sharded); return zk::launch_fold_round_poly(field, cur, (int)m, (int)degree, cur_len, rf, ctx->scratch, ctx->stream, &ctx->launches); });
             cur_len /= 2;
         }
         if (e != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "fold_round_poly"); }

@@ -28,6 +28,7 @@ struct ReduceScratch {
     unsigned* flag_host;     // pinned+mapped completion flag: the last block stores `seq` after the results
     unsigned* flag_host_devptr;
     unsigned seq;            // value the next reducing launch publishes (0 = do not publish)
+    uint64_t* lanes;         // when non-null the reducing launch also widens its result into u64 lanes (sharded all-reduce input)
     int num_sms;
 };
 
@@ -69,11 +70,10 @@ cudaError_t launch_generate(int field, Fe* out, uint64_t count, uint64_t seed, u
 // out[j*G + q] = in[q*L + j]: re-interleave the all-gathered residual shards (q-major) into global order
 cudaError_t launch_interleave(const Fe* in, Fe* out, uint64_t local_len, unsigned world, cudaStream_t stream,
                               int* launches);
-// Widen (D+1) elements into u64 lanes (one 32-bit limb per lane) for an exact ncclSum all-reduce, and the
-// inverse: carry-propagate the lane sums and reduce mod p.
-cudaError_t launch_widen(const Fe* in, uint64_t* lanes, int count, cudaStream_t stream, int* launches);
+// After the exact ncclSum all-reduce of the u64 lanes (one 32-bit limb per lane, written by the reducing
+// launch): carry-propagate the lane sums, reduce mod p, publish result + completion flag.
 cudaError_t launch_narrow(int field, const uint64_t* lanes, Fe* out_dev, Fe* out_host_devptr, int count,
-                          cudaStream_t stream, int* launches);
+                          unsigned* flag_host_devptr, unsigned seq, cudaStream_t stream, int* launches);
 
 // ---- NTT (kernels_ntt.cu) --------------------------------------------------------------------
 struct NttPlan;

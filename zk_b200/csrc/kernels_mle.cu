@@ -102,15 +102,9 @@ __global__ void __launch_bounds__(kThreads) interleave_kernel(const Fe* in, Fe* 
     }
 }
 
-__global__ void widen_kernel(const Fe* in, uint64_t* lanes, int count) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count * 8) lanes[i] = in[i / 8].v[i % 8];
-}
 // lanes hold sums of <= 2^24 32-bit limbs: carry-propagate to a (<= 280-bit) integer, reduce mod p.
 template <class F>
-__global__ void narrow_kernel(const uint64_t* lanes, Fe* out_dev, Fe* out_host, int count) {
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= count) return;
+__device__ __forceinline__ void narrow_one(const uint64_t* lanes, Fe* out_dev, Fe* out_host, int e) {
     uint32_t w[9];
     uint64_t c = 0;
 #pragma unroll
@@ -141,9 +135,20 @@ __global__ void narrow_kernel(const uint64_t* lanes, Fe* out_dev, Fe* out_host, 
     for (int i = 0; i < 8; i++) r.v[i] = w[i];
     out_dev[e] = r;
     out_host[e] = r;
-    __threadfence_system();
 }
 
+template <class F>
+__global__ void narrow_kernel(const uint64_t* lanes, Fe* out_dev, Fe* out_host, int count, unsigned* flag_host,
+                              unsigned seq) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < count) narrow_one<F>(lanes, out_dev, out_host, e);
+    __threadfence_system();
+    __syncwarp();
+    if (threadIdx.x == 0 && seq != 0) {
+        *(volatile unsigned*)flag_host = seq;
+        __threadfence_system();
+    }
+}
 }  // namespace
 
 #define ZK_FIELD_DISPATCH(field, CALL381, CALL377) \
@@ -194,15 +199,10 @@ cudaError_t launch_interleave(const Fe* in, Fe* out, uint64_t local_len, unsigne
     ++*launches;
     return cudaGetLastError();
 }
-cudaError_t launch_widen(const Fe* in, uint64_t* lanes, int count, cudaStream_t stream, int* launches) {
-    widen_kernel<<<1, 128, 0, stream>>>(in, lanes, count);
-    ++*launches;
-    return cudaGetLastError();
-}
 cudaError_t launch_narrow(int field, const uint64_t* lanes, Fe* out_dev, Fe* out_host_devptr, int count,
-                          cudaStream_t stream, int* launches) {
-    ZK_FIELD_DISPATCH(field, (narrow_kernel<Fr381><<<1, 32, 0, stream>>>(lanes, out_dev, out_host_devptr, count)),
-                      (narrow_kernel<Fr377><<<1, 32, 0, stream>>>(lanes, out_dev, out_host_devptr, count)));
+                          unsigned* flag_host_devptr, unsigned seq, cudaStream_t stream, int* launches) {
+    ZK_FIELD_DISPATCH(field, (narrow_kernel<Fr381><<<1, 32, 0, stream>>>(lanes, out_dev, out_host_devptr, count, flag_host_devptr, seq)),
+                      (narrow_kernel<Fr377><<<1, 32, 0, stream>>>(lanes, out_dev, out_host_devptr, count, flag_host_devptr, seq)));
     ++*launches;
     return cudaGetLastError();
 }

@@ -56,6 +56,7 @@ struct ReduceArgs {
     int out_slot;
     unsigned* flag_host;  // mapped pinned word the host spins on (saves a stream synchronisation per round)
     unsigned seq;
+    uint64_t* lanes;      // sharded runs: one 32-bit limb per u64 lane, the input of the exact ncclSum all-reduce
 };
 
 // Block-level reduction of NP per-thread accumulators, then grid-level via last-block-done.
@@ -148,6 +149,10 @@ __device__ __forceinline__ void reduce_publish(Fe* acc, const ReduceArgs& ra) {
         for (int t = 0; t < NP; t++) {
             st_fe(ra.result_dev + ra.out_slot + t, fin[t]);
             st_fe(ra.result_host + ra.out_slot + t, fin[t]);
+            if (ra.lanes) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) ra.lanes[(ra.out_slot + t) * 8 + i] = fin[t].v[i];
+            }
         }
         *ra.ticket = 0;  // ready for the next launch on this stream
         __threadfence_system();
@@ -376,7 +381,7 @@ inline unsigned grid_for(uint64_t items, int threads, int num_sms, int bpsm) {
     return (unsigned)(need < cap ? need : cap);
 }
 inline ReduceArgs make_ra(const ReduceScratch& s, int slot) {
-    return ReduceArgs{s.block_partials, s.ticket, s.result_dev, s.result_host_devptr, slot, s.flag_host_devptr, s.seq};
+    return ReduceArgs{s.block_partials, s.ticket, s.result_dev, s.result_host_devptr, slot, s.flag_host_devptr, s.seq, s.lanes};
 }
 template <class F>
 Fe small_constant(unsigned t);  // Montgomery form of small integer t (host side)
