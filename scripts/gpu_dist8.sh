@@ -14,4 +14,4 @@ for f in ("gpurun_out/bench_8.json","gpurun_out/bench_c4_8.json"):
         print(f, {k:d.get(k) for k in ["value","ms_per_step","verified","proof_keccak","step_ms","gpu_launches","n_gpus"]}, d["config"]["log_n"], d.get("e2e"))
     except Exception as e: print(f, "ERR", e)
 PY
-tail -3 gpurun_out/bench_8.err gpurun_out/bench_c4_8.err
+tail -n 3 gpurun_out/bench_8.err; tail -n 3 gpurun_out/bench_c4_8.err
