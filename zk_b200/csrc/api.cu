@@ -1043,7 +1043,16 @@ int zk_ntt(zk_ctx* ctx, zk_table* inout, int inverse) {
         if (e != cudaSuccess) return cuda_fail(ctx, e, "ntt_plan_create");
         ctx->ntt_plans.push_back(plan);
     }
-    e = zk::ntt_execute(plan, inout->data, ctx->stream, &ctx->launches);
+    Fe* result = nullptr;
+    e = zk::ntt_execute(plan, inout->data, &result, ctx->stream, &ctx->launches);
+    if (e == cudaSuccess && result != inout->data) {
+        if (inout->capacity == inout->local_len) {  // swap buffers with the plan: no copy
+            zk::ntt_plan_adopt_scratch(plan, inout->data);
+            inout->data = result;
+        } else {
+            e = cudaMemcpyAsync(inout->data, result, (size_t)inout->local_len * 32, cudaMemcpyDeviceToDevice, ctx->stream);
+        }
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     count(ctx);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "ntt_execute");

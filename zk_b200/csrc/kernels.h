@@ -80,8 +80,11 @@ struct NttPlan;
 cudaError_t ntt_plan_create(int field, unsigned log_n, bool inverse, cudaStream_t stream, NttPlan** out, int* launches);
 void ntt_plan_destroy(NttPlan*);
 bool ntt_plan_is(const NttPlan*, int field, unsigned log_n, bool inverse);
-// natural order in -> natural order out, in place on `data` (uses plan-owned scratch)
-cudaError_t ntt_execute(NttPlan* plan, Fe* data, cudaStream_t stream, int* launches);
+// natural order in -> natural order out.  `data` is clobbered; *result is where the transform ends up: `data`
+// itself (small sizes) or the plan's N-element scratch buffer, which the caller may keep by handing the plan
+// another N-element buffer in exchange (ntt_plan_adopt_scratch).
+cudaError_t ntt_execute(NttPlan* plan, Fe* data, Fe** result, cudaStream_t stream, int* launches);
+void ntt_plan_adopt_scratch(NttPlan* plan, Fe* buf);
 
 // ---- micro-benchmarks (microbench.cu) ------------------------------------------------------------
 struct MicrobenchResult {

@@ -9,7 +9,9 @@
 // into passes of up to 9: a pass loads tiles of 2^s elements (stride N_b/2^s, 4 adjacent tiles per block so
 // global accesses are 128-byte segments) into shared memory, runs a plain 2^s-point DIF there with the small
 // twiddles w_{2^s}^j, multiplies output c by the inter-pass twiddle w_N^(2^t0 * base * c) and writes back in
-// place (the classic four-step factorisation).  2^28 points: 4 passes over the data instead of 28.
+// place (the classic four-step factorisation).  The last pass writes each element directly to its natural-order
+// (bit-reversed) slot of a second buffer, scaled by N^-1 for the inverse, and the caller swaps the two buffers:
+// 2^28 points take 4 passes over the data instead of 28 + a permutation pass.
 // Any exact algorithm gives bit-identical outputs (integer arithmetic).
 #include "keccak.hpp"  // host_field.hpp
 #include "kernels.h"
@@ -22,6 +24,7 @@ struct NttPlan {
     bool inverse;
     Fe* twiddles;  // w^i, i < N/2 (Montgomery)
     Fe n_inv;      // N^-1 (inverse only)
+    Fe* scratch;   // N elements: the last pass writes the natural-order result here (lazily allocated)
 };
 
 namespace {
@@ -91,7 +94,8 @@ __device__ __forceinline__ void sts_fe(uint4* lo, uint4* hi, unsigned i, const F
 
 template <class F>
 __global__ void __launch_bounds__(kPassThreads)
-    ntt_pass_kernel(Fe* a, const Fe* __restrict__ tw, unsigned log_n, unsigned t0, unsigned s, uint64_t n_groups) {
+    ntt_pass_kernel(Fe* a, const Fe* __restrict__ tw, unsigned log_n, unsigned t0, unsigned s, uint64_t n_groups,
+                    Fe* out_natural, bool scale, Fe n_inv) {
     extern __shared__ uint4 smem[];
     const unsigned tile = 1u << s, elems = tile * kTileB;
     uint4* lo = smem;                 // [elems]   limbs 0-3 of element (x, b) at x*kTileB + b
@@ -143,7 +147,15 @@ __global__ void __launch_bounds__(kPassThreads)
                     else val = fe_mul<F>(val, ld_fe(tw + ex));
                 }
             }
-            st_fe(a + (blk << log_nb) + base + ((uint64_t)x << log_stride), val);
+            const uint64_t g = (blk << log_nb) + base + ((uint64_t)x << log_stride);
+            if (out_natural != nullptr) {
+                // last pass: the element at position g of the in-place DIF is X[bitrev(g)] — write it straight to
+                // its natural-order slot (32-byte sector writes) and fold the N^-1 of the inverse transform in
+                if (scale) val = fe_mul<F>(val, n_inv);
+                st_fe(out_natural + (__brevll(g) >> (64 - log_n)), val);
+            } else {
+                st_fe(a + g, val);
+            }
         }
     }
 }
@@ -177,7 +189,8 @@ cudaError_t plan_build(NttPlan* p, cudaStream_t st, int* launches) {
 }
 
 template <class F>
-cudaError_t execute(NttPlan* p, Fe* data, cudaStream_t st, int* launches) {
+cudaError_t execute(NttPlan* p, Fe* data, Fe** result, cudaStream_t st, int* launches) {
+    *result = data;
     const unsigned k = p->log_n;
     const uint64_t n = (uint64_t)1 << k;
     // split the k stages into ceil(k/9) passes of (almost) equal size, every pass >= 2 stages when k >= 4
@@ -205,21 +218,32 @@ cudaError_t execute(NttPlan* p, Fe* data, cudaStream_t st, int* launches) {
             const uint64_t n_groups = n_tiles / kTileB;
             const size_t smem = (size_t)(2 * ((1u << s) * kTileB) + (1u << s)) * sizeof(uint4);
             const unsigned grid = (unsigned)(n_groups < (uint64_t)sms * 3 ? n_groups : (uint64_t)sms * 3);
-            ntt_pass_kernel<F><<<grid, kPassThreads, smem, st>>>(data, p->twiddles, k, t0, s, n_groups);
+            const bool last = (pi + 1 == n_pass);
+            if (last) {
+                if (!p->scratch) {
+                    cudaError_t ea = cudaMalloc((void**)&p->scratch, (size_t)n * sizeof(Fe));
+                    if (ea != cudaSuccess) return ea;
+                }
+                *result = p->scratch;
+            }
+            ntt_pass_kernel<F><<<grid, kPassThreads, smem, st>>>(data, p->twiddles, k, t0, s, n_groups,
+                                                                last ? p->scratch : nullptr, p->inverse, p->n_inv);
             ++*launches;
         }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         t0 += s;
     }
-    bitrev_kernel<F><<<grid_1d(n), kThreads, 0, st>>>(data, n, k, p->inverse, p->n_inv);
-    ++*launches;
+    if (*result == data) {  // small transforms ran stage by stage in place: separate bit-reversal pass
+        bitrev_kernel<F><<<grid_1d(n), kThreads, 0, st>>>(data, n, k, p->inverse, p->n_inv);
+        ++*launches;
+    }
     return cudaGetLastError();
 }
 }  // namespace
 
 cudaError_t ntt_plan_create(int field, unsigned log_n, bool inverse, cudaStream_t stream, NttPlan** out, int* launches) {
-    NttPlan* p = new NttPlan{field, log_n, inverse, nullptr, Fe{}};
+    NttPlan* p = new NttPlan{field, log_n, inverse, nullptr, Fe{}, nullptr};
     cudaError_t e = field == Fr381::ID ? plan_build<Fr381>(p, stream, launches) : plan_build<Fr377>(p, stream, launches);
     if (e != cudaSuccess) {
         ntt_plan_destroy(p);
@@ -234,11 +258,13 @@ bool ntt_plan_is(const NttPlan* p, int field, unsigned log_n, bool inverse) {
 void ntt_plan_destroy(NttPlan* p) {
     if (!p) return;
     cudaFree(p->twiddles);
+    cudaFree(p->scratch);
     delete p;
 }
-cudaError_t ntt_execute(NttPlan* plan, Fe* data, cudaStream_t stream, int* launches) {
-    return plan->field == Fr381::ID ? execute<Fr381>(plan, data, stream, launches)
-                                    : execute<Fr377>(plan, data, stream, launches);
+cudaError_t ntt_execute(NttPlan* plan, Fe* data, Fe** result, cudaStream_t stream, int* launches) {
+    return plan->field == Fr381::ID ? execute<Fr381>(plan, data, result, stream, launches)
+                                    : execute<Fr377>(plan, data, result, stream, launches);
 }
+void ntt_plan_adopt_scratch(NttPlan* plan, Fe* buf) { plan->scratch = buf; }
 
 }  // namespace zk
