@@ -1,9 +1,11 @@
 // tools/ubench.cu — instruction-level throughput probes for the sm_100a integer pipe (stand-alone binary).
 // Build: nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -o build/ubench tools/ubench.cu
 #include <cstdio>
+#include <cstring>
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "field29.cuh"
+#include "../zk_b200/csrc/host_field.hpp"
 using namespace zk;
 
 constexpr int T = 256;
@@ -268,6 +270,39 @@ __global__ void __launch_bounds__(T) kW5(uint32_t seed, float* sink) {
     if (s == 0.1234567f) sink[0] = s;
 }
 
+// X: fixed-multiplier product vs the general multiplier
+template <class F>
+__global__ void kCheckFixed(unsigned* bad, int n, FixedMul tab, Fe r_mont) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fe a;
+    for (int l = 0; l < 4; l++) {
+        uint64_t u = smix(0x4321 + (uint64_t)i * 4 + l);
+        if (l == 3) u &= 0x0FFFFFFFFFFFFFFFULL;
+        a.v[2 * l] = (uint32_t)u; a.v[2 * l + 1] = (uint32_t)(u >> 32);
+    }
+    if (i == 0) a = fe_zero<F>();
+    if (i == 1) { for (int k = 0; k < 8; k++) a.v[k] = F::p(k); a.v[0] -= 1; }
+    if (i == 2) { a = fe_zero<F>(); a.v[0] = 0xffffffffu; }
+    if (i == 3) { for (int k = 0; k < 8; k++) a.v[k] = 0xffffffffu; a.v[7] = F::p(7) - 1; }
+    Fe expect = fe_mul<F>(a, r_mont), got = fe_mul_fixed<F>(a, tab);
+    bool same = true;
+    for (int k = 0; k < 8; k++) same &= (got.v[k] == expect.v[k]);
+    if (!same) atomicAdd(bad, 1u);
+}
+template <int ILP>
+__global__ void __launch_bounds__(T) kFx(uint32_t seed, Fe* sink, FixedMul tab) {
+    Fe x[ILP];
+    for (int k = 0; k < ILP; k++) { x[k] = fe_one<Fr381>(); x[k].v[0] ^= (seed + threadIdx.x + k) & 0xffff; }
+#pragma unroll 1
+    for (int it = 0; it < 256; it++) {
+#pragma unroll
+        for (int k = 0; k < ILP; k++) x[k] = fe_mul_fixed<Fr381>(x[k], tab);
+    }
+    Fe s = x[0]; for (int k = 1; k < ILP; k++) for (int i = 0; i < 8; i++) s.v[i] ^= x[k].v[i];
+    if (s.v[0] == 0x1234567 && s.v[7] == 0x7654321) sink[0] = s;
+}
+
 template <class L> float run(L&& launch) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;
@@ -286,6 +321,19 @@ int main() {
         kCheck<Fr377><<<4096, 256>>>(bad, 1 << 20);
         unsigned h377 = 0; cudaMemcpy(&h377, bad, 4, cudaMemcpyDeviceToHost);
         printf("mul29 vs fe_mul mismatches over 2^20 pairs: Fr381 %u, Fr377 %u  (%s)\n", h381, h377, cudaGetErrorString(cudaGetLastError()));
+    }
+    FixedMul tab381;
+    for (int fid = 0; fid < 2; fid++) {
+        zk::host::Field HF(fid);
+        zk::host::El r = HF.from_u64(0x123456789abcdefULL);
+        for (int k = 0; k < 5; k++) r = HF.mul(r, HF.add(r, HF.from_u64(77 + k)));  // some dense element
+        FixedMul tab; zk::host::fixed_mul_table(HF, r, tab.v);
+        Fe rm; memcpy(rm.v, r.v, 32);
+        unsigned* bad; cudaMalloc(&bad, 4); cudaMemset(bad, 0, 4);
+        if (fid == 0) { kCheckFixed<Fr381><<<4096, 256>>>(bad, 1 << 20, tab, rm); tab381 = tab; }
+        else kCheckFixed<Fr377><<<4096, 256>>>(bad, 1 << 20, tab, rm);
+        unsigned h = 0; cudaMemcpy(&h, bad, 4, cudaMemcpyDeviceToHost);
+        printf("fe_mul_fixed vs fe_mul mismatches over 2^20 values, field %d: %u (%s)\n", fid, h, cudaGetErrorString(cudaGetLastError()));
     }
     for (int bps : {4, 8}) {
         const int blocks = sms * bps; const double thr = (double)blocks * T;
@@ -324,6 +372,10 @@ int main() {
         printf("M1 mul29 ILP1                 : %7.3f mul/clk/SM  (%.3e mul/s)\n", thr * 256 * 1 / (ms * 1e-3) / sm_clk, thr * 256 * 1 / (ms * 1e-3));
         ms = run([&] { kM<2><<<blocks, T>>>(7, (Fe*)sink); });
         printf("M2 mul29 ILP2                 : %7.3f mul/clk/SM  (%.3e mul/s)\n", thr * 256 * 2 / (ms * 1e-3) / sm_clk, thr * 256 * 2 / (ms * 1e-3));
+        ms = run([&] { kFx<1><<<blocks, T>>>(7, (Fe*)sink, tab381); });
+        printf("X1 fe_mul_fixed ILP1          : %7.3f mul/clk/SM  (%.3e mul/s)\n", thr * 256 * 1 / (ms * 1e-3) / sm_clk, thr * 256 * 1 / (ms * 1e-3));
+        ms = run([&] { kFx<2><<<blocks, T>>>(7, (Fe*)sink, tab381); });
+        printf("X2 fe_mul_fixed ILP2          : %7.3f mul/clk/SM  (%.3e mul/s)\n", thr * 256 * 2 / (ms * 1e-3) / sm_clk, thr * 256 * 2 / (ms * 1e-3));
         ms = run([&] { kE<1, false><<<blocks, T>>>(7, (Fe*)sink); });
         printf("E1 fe_mul ILP1                : %7.3f mul/clk/SM  (%.3e mul/s)\n", thr * 256 * 1 / (ms * 1e-3) / sm_clk, thr * 256 * 1 / (ms * 1e-3));
         ms = run([&] { kE<2, false><<<blocks, T>>>(7, (Fe*)sink); });

@@ -74,6 +74,11 @@ struct Fr377 {
     }
 };
 
+// Precomputed multiples of a launch-wide multiplier (see fe_mul_fixed): v[i] = r * 2^(32 i + 64) mod p.
+struct FixedMul {
+    uint32_t v[8][8];
+};
+
 #ifdef __CUDACC__
 
 // ---- 256-bit global memory access (sm_100+: LDG.E.ENL2.256 / STG.E.ENL2.256) ------------------
@@ -399,6 +404,104 @@ __device__ __noinline__ Fe fe_redc_wide(const uint32_t* vin) {
         k.v[i] = F::k288(i);
     }
     return fe_mul<F>(fe_reduce_once<F>(u), k);
+}
+
+
+// ---- multiplication by a launch-wide constant (the fold challenge r) ---------------------------------------
+// Every fold of a round multiplies by the SAME r, so the host precomputes the eight multiples
+//     tab.v[i] = r * 2^(32 i + 64) mod p          (plain integers, r canonical; host_field.hpp::fixed_mul_table)
+// and x*r = sum_i x_i * tab[i] needs no interleaved reduction: eight ALIGNED rows (64 wide multiplies) give a
+// sum < 2^290, two Montgomery rows divide the pre-scaled sum by 2^64 (result < 2p), one conditional subtract.
+// 76 (Fr381) / 78 (Fr377) wide multiplies instead of 112 / 120.  For x = aR (Montgomery form) the result is the
+// canonical residue (a r)R — bit-identical to fe_mul(x, rR).
+namespace detail {
+// One Montgomery row on U[0..8] (+U[9] if TOP): U += m*p with m = -U[0]; afterwards U[0] is (logically) zero.
+template <class F, bool TOP>
+__device__ __forceinline__ void redc_row_inplace(uint32_t* U) {
+    const uint32_t t0 = U[0];
+    uint32_t m;
+    asm volatile("sub.u32 %0, 0, %1;" : "=r"(m) : "r"(t0));
+    uint32_t top = TOP ? U[9] : 0u;
+    // chain A: columns 1.. : the carry of column 0 (t0 + m*p0 = 2^32 * (t0 != 0)), m*p1 and the odd-column products
+    if (F::p(1) == 0xffffffffu) {
+        uint32_t b, s1, h2;
+        asm("min.u32 %0, %1, 1;" : "=r"(b) : "r"(t0));
+        const uint32_t mb = m - b;  // hi(m*p1); lo(m*p1) = t0
+        asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(s1), "=r"(h2) : "r"(t0), "r"(b), "r"(mb));
+        asm("add.cc.u32 %0, %0, %9;\n\t"
+            "addc.cc.u32 %1, %1, %10;\n\t"
+            "madc.lo.cc.u32 %2, %11, %14, %2;\n\t"
+            "madc.hi.cc.u32 %3, %11, %14, %3;\n\t"
+            "madc.lo.cc.u32 %4, %12, %14, %4;\n\t"
+            "madc.hi.cc.u32 %5, %12, %14, %5;\n\t"
+            "madc.lo.cc.u32 %6, %13, %14, %6;\n\t"
+            "madc.hi.cc.u32 %7, %13, %14, %7;\n\t"
+            "addc.u32 %8, %8, 0;"
+            : "+r"(U[1]), "+r"(U[2]), "+r"(U[3]), "+r"(U[4]), "+r"(U[5]), "+r"(U[6]), "+r"(U[7]), "+r"(U[8]), "+r"(top)
+            : "r"(s1), "r"(h2), "r"(F::p(3)), "r"(F::p(5)), "r"(F::p(7)), "r"(m));
+    } else {
+        uint32_t dead = t0;
+        asm("add.cc.u32 %0, %0, %14;\n\t"
+            "madc.lo.cc.u32 %1, %10, %14, %1;\n\t"
+            "madc.hi.cc.u32 %2, %10, %14, %2;\n\t"
+            "madc.lo.cc.u32 %3, %11, %14, %3;\n\t"
+            "madc.hi.cc.u32 %4, %11, %14, %4;\n\t"
+            "madc.lo.cc.u32 %5, %12, %14, %5;\n\t"
+            "madc.hi.cc.u32 %6, %12, %14, %6;\n\t"
+            "madc.lo.cc.u32 %7, %13, %14, %7;\n\t"
+            "madc.hi.cc.u32 %8, %13, %14, %8;\n\t"
+            "addc.u32 %9, %9, 0;"
+            : "+r"(dead), "+r"(U[1]), "+r"(U[2]), "+r"(U[3]), "+r"(U[4]), "+r"(U[5]), "+r"(U[6]), "+r"(U[7]), "+r"(U[8]),
+              "+r"(top)
+            : "r"(F::p(1)), "r"(F::p(3)), "r"(F::p(5)), "r"(F::p(7)), "r"(m));
+    }
+    // chain B: the even-column products p2, p4, p6 at columns (2,3), (4,5), (6,7), then ripple
+    asm("mad.lo.cc.u32 %0, %8, %11, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %11, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %11, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %11, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %11, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %11, %5;\n\t"
+        "addc.cc.u32 %6, %6, 0;\n\t"
+        "addc.u32 %7, %7, 0;"
+        : "+r"(U[2]), "+r"(U[3]), "+r"(U[4]), "+r"(U[5]), "+r"(U[6]), "+r"(U[7]), "+r"(U[8]), "+r"(top)
+        : "r"(F::p(2)), "r"(F::p(4)), "r"(F::p(6)), "r"(m));
+    if (TOP) U[9] = top;
+}
+}  // namespace detail
+
+template <class F>
+__device__ __forceinline__ Fe fe_mul_fixed(const Fe& x, const FixedMul& tab) {
+    uint32_t E[9], O[9];  // E[j] = column j, O[j] = column j+1; [8] collects the chain carries
+    detail::mul4(E, tab.v[0][0], tab.v[0][2], tab.v[0][4], tab.v[0][6], x.v[0]);
+    detail::mul4(O, tab.v[0][1], tab.v[0][3], tab.v[0][5], tab.v[0][7], x.v[0]);
+    E[8] = 0;
+    O[8] = 0;
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+        detail::cmad4(E, tab.v[i][0], tab.v[i][2], tab.v[i][4], tab.v[i][6], x.v[i], E[8]);
+        detail::cmad4(O, tab.v[i][1], tab.v[i][3], tab.v[i][5], tab.v[i][7], x.v[i], O[8]);
+    }
+    uint32_t T[10];
+    T[0] = E[0];
+    asm("add.cc.u32 %0,%9,%17;\n\taddc.cc.u32 %1,%10,%18;\n\taddc.cc.u32 %2,%11,%19;\n\taddc.cc.u32 %3,%12,%20;\n\t"
+        "addc.cc.u32 %4,%13,%21;\n\taddc.cc.u32 %5,%14,%22;\n\taddc.cc.u32 %6,%15,%23;\n\taddc.cc.u32 %7,%16,%24;\n\t"
+        "addc.u32 %8,%25,0;"
+        : "=r"(T[1]), "=r"(T[2]), "=r"(T[3]), "=r"(T[4]), "=r"(T[5]), "=r"(T[6]), "=r"(T[7]), "=r"(T[8]), "=r"(T[9])
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(O[0]), "r"(O[1]),
+          "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]));
+    detail::redc_row_inplace<F, true>(T);       // columns 0..9 -> value in columns 1..9
+    detail::redc_row_inplace<F, false>(T + 1);  // columns 1..9 -> value in columns 2..9, < 2p
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = T[2 + i];
+    return fe_reduce_once<F>(r);
+}
+
+// fold with the precomputed multiples of the challenge: l - r*(l - h)
+template <class F>
+__device__ __forceinline__ Fe fe_fold_fixed(const Fe& l, const Fe& h, const FixedMul& tab) {
+    return fe_sub<F>(l, fe_mul_fixed<F>(fe_sub<F>(l, h), tab));
 }
 
 // Montgomery form <-> canonical integer (ark-ff `into_bigint` / `from_bigint`)

@@ -145,5 +145,21 @@ class Field {
     const FieldParams& P;
 };
 
+// Multiples of a launch-wide multiplier for the device's fe_mul_fixed: out[i] = r * 2^(32 i + 64) mod p as plain
+// (canonical, non-Montgomery) 8x32-bit limbs.  `r_mont` is r in Montgomery form.
+inline void fixed_mul_table(const Field& F, const El& r_mont, uint32_t out[8][8]) {
+    El two32 = F.from_u64((uint64_t)1 << 32);
+    El cur = F.mul(r_mont, F.mul(two32, two32));  // r * 2^64 (Montgomery form)
+    for (int i = 0; i < 8; i++) {
+        uint64_t c[4];
+        F.to_canonical(cur, c);
+        for (int j = 0; j < 4; j++) {
+            out[i][2 * j] = (uint32_t)c[j];
+            out[i][2 * j + 1] = (uint32_t)(c[j] >> 32);
+        }
+        cur = F.mul(cur, two32);
+    }
+}
+
 }  // namespace host
 }  // namespace zk

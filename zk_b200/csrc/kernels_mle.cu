@@ -2,6 +2,7 @@
 // element-wise product, canonical big-endian serialisation, Montgomery conversion, the synthetic
 // table generator and the multi-GPU glue kernels.  Reference call sites cited per kernel.
 #include "kernels.h"
+#include "host_field.hpp"
 
 namespace zk {
 namespace {
@@ -18,12 +19,13 @@ inline unsigned grid_1d(uint64_t items, unsigned cap = 148 * 16) {
 // (polynomial/src/multilinear/evaluation_form.rs:54-72; pair addressing pairing_index.rs:2-21):
 // out[k] = L - a (L - R), L = in[insert_bit(k,pos,0)], R = in[L_index | 1<<pos].
 template <class F>
-__global__ void __launch_bounds__(kThreads) fold_var_kernel(const Fe* in, Fe* out, uint64_t pairs, unsigned pos, Fe a) {
+__global__ void __launch_bounds__(kThreads)
+    fold_var_kernel(const Fe* in, Fe* out, uint64_t pairs, unsigned pos, const __grid_constant__ FixedMul atab) {
     const uint64_t stride = (uint64_t)gridDim.x * kThreads, low_mask = ((uint64_t)1 << pos) - 1;
     for (uint64_t k = (uint64_t)blockIdx.x * kThreads + threadIdx.x; k < pairs; k += stride) {
         uint64_t l = ((k >> pos) << (pos + 1)) | (k & low_mask);
         Fe L = ld_fe(in + l), R = ld_fe(in + (l | ((uint64_t)1 << pos)));
-        st_fe(out + k, fe_fold<F>(L, R, a));
+        st_fe(out + k, fe_fold_fixed<F>(L, R, atab));
     }
 }
 
@@ -161,8 +163,13 @@ cudaError_t launch_fold_var(int field, const Fe* in, Fe* out, unsigned nv, unsig
                             cudaStream_t stream, int* launches) {
     const unsigned pos = nv - 1 - initial_var;
     const uint64_t pairs = (uint64_t)1 << (nv - 1);
-    ZK_FIELD_DISPATCH(field, (fold_var_kernel<Fr381><<<grid_1d(pairs), kThreads, 0, stream>>>(in, out, pairs, pos, a)),
-                      (fold_var_kernel<Fr377><<<grid_1d(pairs), kThreads, 0, stream>>>(in, out, pairs, pos, a)));
+    host::Field HF(field);
+    host::El am;
+    std::memcpy(am.v, a.v, 32);
+    FixedMul atab;
+    host::fixed_mul_table(HF, am, atab.v);  // the assignment is the same for every pair: fe_mul_fixed
+    ZK_FIELD_DISPATCH(field, (fold_var_kernel<Fr381><<<grid_1d(pairs), kThreads, 0, stream>>>(in, out, pairs, pos, atab)),
+                      (fold_var_kernel<Fr377><<<grid_1d(pairs), kThreads, 0, stream>>>(in, out, pairs, pos, atab)));
     ++*launches;
     return cudaGetLastError();
 }

@@ -17,6 +17,7 @@
 // global memory -> the last block to finish (atomic ticket) folds the partials and publishes the
 // D+1 evaluations to device memory and to mapped pinned host memory.
 #include "kernels.h"
+#include "host_field.hpp"
 
 namespace zk {
 namespace {
@@ -219,7 +220,7 @@ __device__ __forceinline__ Fe accw_reduce(const uint4* a) {
 // The four sums are mapped back to S(0..3) by exact field arithmetic in the last block (toom_to_evals).
 template <class F, int D, bool FOLD, bool TOOM = false>
 __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
-    round_kernel(TablePtrs tabs, int m, uint64_t q, Fe r_param, ReduceArgs ra) {
+    round_kernel(TablePtrs tabs, int m, uint64_t q, const __grid_constant__ FixedMul rtab, ReduceArgs ra) {
     static_assert(!TOOM || D == 3, "the Toom point set is wired for cubics");
     extern __shared__ uint4 accw_all[];  // [(D+1)][5][kThreads]
     __shared__ Fe* s_tab[kMaxFactors];
@@ -227,9 +228,6 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
     accw_zero(accw_all, D + 1);
     __syncthreads();
     uint4* accw = accw_all + threadIdx.x;  // + t * 5 * kThreads + word_group * kThreads
-    Fe r;  // the challenge, pinned into registers (a constant-bank multiplier operand defeats IMAD.WIDE fusion)
-#pragma unroll
-    for (int i = 0; i < 8; i++) asm volatile("mov.u32 %0, %1;" : "=r"(r.v[i]) : "r"(r_param.v[i]));
     const uint64_t stride = (uint64_t)gridDim.x * kThreads;
     const uint64_t j0 = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
     // Round 0 (no fold) software-pipelines its loads: the pair of the next (item, factor) is in flight while this
@@ -251,9 +249,9 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
             if (FOLD) {  // T has 4q entries: fold (j, j+2q) and (j+q, j+3q) at r, write back to j and j+q
                 Fe x0 = ld_fe_stream(T + j), x2 = ld_fe_stream(T + j + 2 * q);
                 Fe x1 = ld_fe_stream(T + j + q), x3 = ld_fe_stream(T + j + 3 * q);
-                lo = fe_fold<F>(x0, x2, r);
+                lo = fe_fold_fixed<F>(x0, x2, rtab);  // the challenge enters as precomputed multiples (fe_mul_fixed)
                 st_fe(T + j, lo);
-                hi = fe_fold<F>(x1, x3, r);
+                hi = fe_fold_fixed<F>(x1, x3, rtab);
                 st_fe(T + j + q, hi);
             } else {  // T has 2q entries: the pair is (j, j+q)
                 lo = n0;
@@ -323,12 +321,12 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
 
 // grid.y = factor index
 template <class F>
-__global__ void __launch_bounds__(256) fold_kernel(TablePtrs tabs, uint64_t half, Fe r) {
+__global__ void __launch_bounds__(256) fold_kernel(TablePtrs tabs, uint64_t half, const __grid_constant__ FixedMul rtab) {
     Fe* T = tabs.t[blockIdx.y];
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < half; j += stride) {
         Fe l = ld_fe_stream(T + j), h = ld_fe_stream(T + j + half);
-        st_fe(T + j, fe_fold<F>(l, h, r));
+        st_fe(T + j, fe_fold_fixed<F>(l, h, rtab));
     }
 }
 
@@ -386,6 +384,17 @@ inline ReduceArgs make_ra(const ReduceScratch& s, int slot) {
 template <class F>
 Fe small_constant(unsigned t);  // Montgomery form of small integer t (host side)
 
+// host: the multiples r * 2^(32 i + 64) mod p the kernels' fe_mul_fixed consumes (r in Montgomery form)
+template <class F>
+FixedMul make_fixed(const Fe& r) {
+    host::Field HF(F::ID);
+    host::El rm;
+    std::memcpy(rm.v, r.v, 32);
+    FixedMul t;
+    host::fixed_mul_table(HF, rm, t.v);
+    return t;
+}
+
 template <class F, int D, bool FOLD, bool TOOM = false>
 cudaError_t do_round(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st) {
     constexpr size_t smem = (size_t)(D + 1) * 5 * kThreads * sizeof(uint4);
@@ -396,7 +405,7 @@ cudaError_t do_round(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, cons
         return nb;
     }();
     unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
-    round_kernel<F, D, FOLD, TOOM><<<grid, kThreads, smem, st>>>(tabs, m, q, r, make_ra(s, 0));
+    round_kernel<F, D, FOLD, TOOM><<<grid, kThreads, smem, st>>>(tabs, m, q, make_fixed<F>(r), make_ra(s, 0));
     return cudaGetLastError();
 }
 template <class F, bool FOLD>
@@ -452,7 +461,7 @@ cudaError_t fold_dispatch(const TablePtrs& tabs, int m, uint64_t half, const Fe&
     uint64_t need = (half + 255) / 256;
     uint64_t cap = (uint64_t)num_sms * 8;
     dim3 grid((unsigned)(need < cap ? (need ? need : 1) : cap), (unsigned)m);
-    fold_kernel<F><<<grid, 256, 0, st>>>(tabs, half, r);
+    fold_kernel<F><<<grid, 256, 0, st>>>(tabs, half, make_fixed<F>(r));
     ++*launches;
     return cudaGetLastError();
 }
