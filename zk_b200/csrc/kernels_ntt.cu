@@ -25,6 +25,7 @@ struct NttPlan {
     Fe* twiddles;  // w^i, i < N/2 (Montgomery)
     Fe n_inv;      // N^-1 (inverse only)
     Fe* scratch;   // N elements: the last pass writes the natural-order result here (lazily allocated)
+    FixedMul n_inv_tab;  // multiples of N^-1 for fe_mul_fixed (inverse only)
 };
 
 namespace {
@@ -95,7 +96,7 @@ __device__ __forceinline__ void sts_fe(uint4* lo, uint4* hi, unsigned i, const F
 template <class F>
 __global__ void __launch_bounds__(kPassThreads)
     ntt_pass_kernel(Fe* a, const Fe* __restrict__ tw, unsigned log_n, unsigned t0, unsigned s, uint64_t n_groups,
-                    Fe* out_natural, bool scale, Fe n_inv) {
+                    Fe* out_natural, bool scale, const __grid_constant__ FixedMul n_inv_tab) {
     extern __shared__ uint4 smem[];
     const unsigned tile = 1u << s, elems = tile * kTileB;
     uint4* lo = smem;                 // [elems]   limbs 0-3 of element (x, b) at x*kTileB + b
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(kPassThreads)
             if (out_natural != nullptr) {
                 // last pass: the element at position g of the in-place DIF is X[bitrev(g)] — write it straight to
                 // its natural-order slot (32-byte sector writes) and fold the N^-1 of the inverse transform in
-                if (scale) val = fe_mul<F>(val, n_inv);
+                if (scale) val = fe_mul_fixed<F>(val, n_inv_tab);
                 st_fe(out_natural + (__brevll(g) >> (64 - log_n)), val);
             } else {
                 st_fe(a + g, val);
@@ -168,6 +169,7 @@ cudaError_t plan_build(NttPlan* p, cudaStream_t st, int* launches) {
         w = HF.inverse(w);
         host::El ninv = HF.inverse(HF.from_u64((uint64_t)1 << p->log_n));
         std::memcpy(p->n_inv.v, ninv.v, 32);
+        host::fixed_mul_table(HF, ninv, p->n_inv_tab.v);
     }
     const uint64_t half_n = (uint64_t)1 << (p->log_n - 1);
     cudaError_t e = cudaMalloc((void**)&p->twiddles, (size_t)half_n * sizeof(Fe));
@@ -227,7 +229,7 @@ cudaError_t execute(NttPlan* p, Fe* data, Fe** result, cudaStream_t st, int* lau
                 *result = p->scratch;
             }
             ntt_pass_kernel<F><<<grid, kPassThreads, smem, st>>>(data, p->twiddles, k, t0, s, n_groups,
-                                                                last ? p->scratch : nullptr, p->inverse, p->n_inv);
+                                                                last ? p->scratch : nullptr, p->inverse, p->n_inv_tab);
             ++*launches;
         }
         cudaError_t e = cudaGetLastError();
@@ -243,7 +245,7 @@ cudaError_t execute(NttPlan* p, Fe* data, Fe** result, cudaStream_t st, int* lau
 }  // namespace
 
 cudaError_t ntt_plan_create(int field, unsigned log_n, bool inverse, cudaStream_t stream, NttPlan** out, int* launches) {
-    NttPlan* p = new NttPlan{field, log_n, inverse, nullptr, Fe{}, nullptr};
+    NttPlan* p = new NttPlan{field, log_n, inverse, nullptr, Fe{}, nullptr, FixedMul{}};
     cudaError_t e = field == Fr381::ID ? plan_build<Fr381>(p, stream, launches) : plan_build<Fr377>(p, stream, launches);
     if (e != cudaSuccess) {
         ntt_plan_destroy(p);

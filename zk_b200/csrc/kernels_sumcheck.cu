@@ -334,16 +334,17 @@ __global__ void __launch_bounds__(256) fold_kernel(TablePtrs tabs, uint64_t half
 // sum_j prod_k [lo_k - t (lo_k - hi_k)]   (t given in Montgomery form; is_zero/is_one shortcuts are
 // the same field function, evaluation_form.rs:61-62).
 template <class F>
-__global__ void __launch_bounds__(kThreads) eval_at_kernel(TablePtrs tabs, int m, uint64_t half, Fe t, ReduceArgs ra) {
+__global__ void __launch_bounds__(kThreads)
+    eval_at_kernel(TablePtrs tabs, int m, uint64_t half, const __grid_constant__ FixedMul ttab, ReduceArgs ra) {
     Fe acc[1];
     acc[0] = fe_zero<F>();
     const uint64_t stride = (uint64_t)gridDim.x * kThreads;
 #pragma unroll 1
     for (uint64_t j = (uint64_t)blockIdx.x * kThreads + threadIdx.x; j < half; j += stride) {
-        Fe pr = fe_fold<F>(ld_fe_stream(tabs.t[0] + j), ld_fe_stream(tabs.t[0] + j + half), t);
+        Fe pr = fe_fold_fixed<F>(ld_fe_stream(tabs.t[0] + j), ld_fe_stream(tabs.t[0] + j + half), ttab);
 #pragma unroll 1
         for (int k = 1; k < m; k++)
-            pr = fe_mul<F>(pr, fe_fold<F>(ld_fe_stream(tabs.t[k] + j), ld_fe_stream(tabs.t[k] + j + half), t));
+            pr = fe_mul<F>(pr, fe_fold_fixed<F>(ld_fe_stream(tabs.t[k] + j), ld_fe_stream(tabs.t[k] + j + half), ttab));
         acc[0] = fe_add<F>(acc[0], pr);
     }
     reduce_publish<F, 1>(acc, ra);
@@ -447,7 +448,7 @@ cudaError_t round_poly_dispatch(const TablePtrs& tabs, int m, int degree, uint64
     for (int t = 0; t <= degree; t++) {
         ReduceArgs ra = make_ra(s, t);
         if (t != degree) ra.seq = 0;  // only the last launch of the group publishes the completion flag
-        eval_at_kernel<F><<<grid, kThreads, 0, st>>>(tabs, m, half, host_small_mont<F>((unsigned)t), ra);
+        eval_at_kernel<F><<<grid, kThreads, 0, st>>>(tabs, m, half, make_fixed<F>(host_small_mont<F>((unsigned)t)), ra);
         ++*launches;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
