@@ -305,13 +305,26 @@ def run_ours(args):
     fused_s = (sum(fused_ms) / len(fused_ms)) * 1e-3
     achieved = fused_bytes / fused_s / 1e9
     fused_muls = (2 * m + (d + 1) * (m - 1)) * (local_n0 // 4)
+    # IMAD.WIDE.U32 actually issued per item of the fused step (field.cuh): a fold is a fixed-multiplier product
+    # (76), an intermediate product 112, the last product of a term 64 (unreduced); the cubic/3-factor case
+    # carries its terms at the Toom points (3 intermediate products instead of 4)
+    if m == 1:
+        prod_wide = 0
+    elif m == 3 and d == 3:
+        prod_wide = 3 * 112 + 4 * 64
+    else:
+        prod_wide = (m - 2) * (d + 1) * 112 + (d + 1) * 64
+    wide_per_item = 2 * m * 76 + prod_wide
+    wide_per_s = wide_per_item * (local_n0 // 4) / fused_s
     mb = ctx.microbench(FIELD) if not args.no_microbench else {"fe_mul_per_s": float("nan"), "imad_wide_per_s": float("nan")}
     roofline = {"bound": "hbm", "kernel": f"round_kernel<Fr381,{d},FOLD=true> (first fused fold+round-sum step, m={m})", "achieved": achieved,
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_src,
                 "traffic": None, "algorithmic_bytes_per_launch": fused_bytes, "launch_ms": fused_s * 1e3,
-                "int_pipe": {"field_mul_per_s": fused_muls / fused_s, "standalone_fe_mul_per_s_peak": mb["fe_mul_per_s"],
-                             "frac_of_standalone_mul_peak": fused_muls / fused_s / mb["fe_mul_per_s"],
-                             "imad_wide_per_s_peak": mb["imad_wide_per_s"]},
+                "int_pipe": {"bound": "IMAD.WIDE.U32 issue rate (half-rate integer multiply pipe)", "imad_wide_per_item": wide_per_item,
+                             "achieved_imad_wide_per_s": wide_per_s, "peak_imad_wide_per_s": mb["imad_wide_per_s"],
+                             "frac": wide_per_s / mb["imad_wide_per_s"], "field_mul_per_s": fused_muls / fused_s,
+                             "frac_textbook_128_per_mul": fused_muls / fused_s * 128 / mb["imad_wide_per_s"],
+                             "standalone_fe_mul_per_s": mb["fe_mul_per_s"]},
                 "whole_prove": {"alg_bytes": alg_bytes(n, m) / world, "gbs": alg_bytes(n, m) / world / (ms_per_step * 1e-3) / 1e9}}
 
     # ---- CPU baseline beside it (bounded sample, rank 0, N = 1 only) ----------------------------------------------
