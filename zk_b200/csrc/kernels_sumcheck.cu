@@ -233,11 +233,22 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
     // Round 0 (no fold) software-pipelines its loads: the pair of the next (item, factor) is in flight while this
     // one is multiplied (+6 % on that kernel).  The fused kernel does not: the four extra elements cost 32
     // registers and measured slower.
-    constexpr bool kPrefetch = !FOLD;
-    Fe n0, n1;
-    if (kPrefetch && j0 < q) {
-        n0 = ld_fe_stream(s_tab[0] + j0);
-        n1 = ld_fe_stream(s_tab[0] + j0 + q);
+    // Software pipelining of the global loads.  Round 0 (no fold) keeps the pair of the next (item, factor) in
+    // flight while this one is multiplied.  The fused kernel issues the four loads of the next (item, factor)
+    // right AFTER this factor's folds (when x0..x3 are dead) so they land during the product multiplications
+    // (-4 % at D = 3; at D <= 2 the register budget of the higher-occupancy variants makes it a loss).
+    constexpr bool kFoldPrefetch = FOLD && D >= 3;
+    Fe n0, n1, n2, n3;
+    if (j0 < q) {
+        Fe* T = s_tab[0];
+        if (FOLD) {
+            if (kFoldPrefetch) {
+                n0 = ld_fe_stream(T + j0); n2 = ld_fe_stream(T + j0 + 2 * q); n1 = ld_fe_stream(T + j0 + q); n3 = ld_fe_stream(T + j0 + 3 * q);
+            }
+        } else {
+            n0 = ld_fe_stream(T + j0);
+            n1 = ld_fe_stream(T + j0 + q);
+        }
     }
 #pragma unroll 1
     for (uint64_t j = j0; j < q; j += stride) {
@@ -246,20 +257,31 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
         for (int k = 0; k < m; k++) {
             Fe* T = s_tab[k];
             Fe lo, hi;
+            const bool more_k = (k + 1 < m);
+            const uint64_t nj = more_k ? j : j + stride;
+            Fe* NT = s_tab[more_k ? k + 1 : 0];
             if (FOLD) {  // T has 4q entries: fold (j, j+2q) and (j+q, j+3q) at r, write back to j and j+q
-                Fe x0 = ld_fe_stream(T + j), x2 = ld_fe_stream(T + j + 2 * q);
-                Fe x1 = ld_fe_stream(T + j + q), x3 = ld_fe_stream(T + j + 3 * q);
-                lo = fe_fold_fixed<F>(x0, x2, rtab);  // the challenge enters as precomputed multiples (fe_mul_fixed)
-                st_fe(T + j, lo);
-                hi = fe_fold_fixed<F>(x1, x3, rtab);
-                st_fe(T + j + q, hi);
+                if (kFoldPrefetch) {
+                    lo = fe_fold_fixed<F>(n0, n2, rtab);  // the challenge enters as precomputed multiples (fe_mul_fixed)
+                    st_fe(T + j, lo);
+                    hi = fe_fold_fixed<F>(n1, n3, rtab);
+                    st_fe(T + j + q, hi);
+                    if (nj < q) {
+                        n0 = ld_fe_stream(NT + nj); n2 = ld_fe_stream(NT + nj + 2 * q);
+                        n1 = ld_fe_stream(NT + nj + q); n3 = ld_fe_stream(NT + nj + 3 * q);
+                    }
+                } else {
+                    Fe x0 = ld_fe_stream(T + j), x2 = ld_fe_stream(T + j + 2 * q);
+                    Fe x1 = ld_fe_stream(T + j + q), x3 = ld_fe_stream(T + j + 3 * q);
+                    lo = fe_fold_fixed<F>(x0, x2, rtab);
+                    st_fe(T + j, lo);
+                    hi = fe_fold_fixed<F>(x1, x3, rtab);
+                    st_fe(T + j + q, hi);
+                }
             } else {  // T has 2q entries: the pair is (j, j+q)
                 lo = n0;
                 hi = n1;
-                const bool more_k = (k + 1 < m);
-                const uint64_t nj = more_k ? j : j + stride;
                 if (nj < q) {
-                    Fe* NT = s_tab[more_k ? k + 1 : 0];
                     n0 = ld_fe_stream(NT + nj);
                     n1 = ld_fe_stream(NT + nj + q);
                 }
