@@ -166,6 +166,15 @@ ZK_API int zk_sumcheck_verify(zk_ctx* ctx, const zk_table* const* tables, unsign
 ZK_API int zk_sumcheck_verify_partial(int field, const uint64_t sum[4], const uint64_t* round_polys, unsigned n_rounds,
                                unsigned degree, uint64_t subclaim_sum_out[4], uint64_t* challenges_out);
 
+/* Proof dump for parity diffing (the reference defines no serialiser for SumcheckProof, lib.rs:8-11; layout of
+ * SURVEY.md Appendix A.5): BE32(sum) || BE32(S_i(t)) for every round i, t = 0..degree || BE32(challenges) ||
+ * BE32(final evaluations); the last two parts are omitted when their pointer is NULL.  Host only.  Writes the
+ * byte count to *out_len (call with out == NULL to size the buffer) and, if digest_out != NULL, the Keccak-256
+ * of the dump. */
+ZK_API int zk_sumcheck_proof_dump(int field, const uint64_t sum[4], const uint64_t* round_polys, unsigned n_rounds,
+                           unsigned degree, const uint64_t* challenges, const uint64_t* final_evals, unsigned m,
+                           uint8_t* out, size_t out_cap, size_t* out_len, uint8_t digest_out[32]);
+
 /* ---- transcript  (transcript/src/lib.rs) — host Keccak-256 -------------------------------------- */
 ZK_API zk_transcript* zk_transcript_new(void);                                             /* :10 */
 ZK_API void zk_transcript_free(zk_transcript* t);

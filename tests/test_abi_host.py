@@ -155,3 +155,16 @@ def test_verify_partial_host_vs_golden(zk, golden):
     bad = zk.SumcheckProof.from_values(0, 12, [[hx(x) for x in r] for r in c["round_polys"]])
     with pytest.raises(zk.ZkError, match="claimed_sum != p\\(0\\) \\+ p\\(1\\)"):
         zk.SumcheckVerifier.verify_partial(bad)
+
+
+def test_proof_dump_layout(zk, golden):
+    """zk_sumcheck_proof_dump: BE32(sum) || rounds || challenges || finals, host only."""
+    c = {x["name"]: x for x in golden["seeded_cases"]}["seeded_n4_m3_d3_partial"]
+    F = O.FIELDS[c["field"]]
+    rps = [[hx(x) for x in r] for r in c["round_polys"]]
+    chs, fins = [hx(x) for x in c["challenges"]], [hx(x) for x in c["finals"]]
+    proof = zk.SumcheckProof.from_values(c["field"], hx(c["claim"]), rps)
+    exp = F.to_bytes_be(hx(c["claim"])) + b"".join(F.to_bytes_be(x) for r in rps for x in r)
+    assert proof.to_bytes() == exp
+    exp_full = exp + b"".join(F.to_bytes_be(x) for x in chs) + b"".join(F.to_bytes_be(x) for x in fins)
+    assert proof.to_bytes(chs, fins) == exp_full

@@ -181,6 +181,38 @@ def test_prove_partial_vs_c_oracle(zk, ctx, cref, fid, n, m, d):
     assert prover.final_evals == cref.mont_to_ints(fid, fin)
 
 
+def test_zero_variable_and_tiny_products(zk, ctx):
+    """n_vars = 0: the prover loop runs zero rounds (`for _ in 0..poly.n_vars()`, prover.rs:44); n = 1: one round."""
+    pp = zk.ProductPoly.new([zk.MultiLinearPolynomial.new(0, [5]), zk.MultiLinearPolynomial.new(0, [7])])
+    assert pp.sum() == 35 and pp.evaluate([]) == 35
+    prover = zk.SumcheckProver(2)
+    proof, chs = prover.prove_partial(pp, 35)
+    assert proof.round_polys == [] and chs == [] and prover.final_evals == [5, 7]
+    sub = zk.SumcheckVerifier.verify_partial(proof)
+    assert sub.sum == 35 and sub.challenges == []
+    pp1 = zk.ProductPoly.new([zk.MultiLinearPolynomial.new(1, [2, 3]), zk.MultiLinearPolynomial.new(1, [4, 6])])
+    O1 = O.ProductPoly([O.MultiLinearPolynomial(F, 1, [2, 3]), O.MultiLinearPolynomial(F, 1, [4, 6])])
+    ref, rch = O.SumcheckProver(2).prove_partial(O1, 26)
+    proof, chs = zk.SumcheckProver(2).prove_partial(pp1, 26)
+    assert proof.round_polys == ref.round_polys and chs == rch
+
+
+def test_prove_with_absorb_multi_chunk(zk, ctx, cref):
+    """prove() on tables larger than one 32 MiB absorb chunk (2^21 entries = 64 MiB per factor): the double-buffered
+    device->host serialisation must hash exactly poly.to_bytes()."""
+    n = 21
+    refs = [cref.gen_table(0, 3, k, n) for k in range(2)]
+    claim = cref.product_sum(0, refs, n)
+    init = b"".join(cref.to_bytes(0, t) for t in refs)
+    rp, ch, fin = cref.prove(0, refs, n, 2, claim, False, fast=True)  # only for shape; transcript differs
+    pp = zk.ProductPoly.new(gpu_tables(zk, 0, 3, n, 2))
+    claim_int = cref.mont_to_ints(0, claim.reshape(1, 4))[0]
+    proof = zk.SumcheckProver(2).prove(pp.clone(), claim_int)
+    rc, sub, vch = cref.verify_internal(0, claim, proof._round_polys_mont, init)  # oracle verifier replays the absorb
+    assert rc == 0
+    assert zk.SumcheckVerifier.verify(pp, proof) is True
+
+
 def test_config1_prove_verify_2p20(zk, ctx, cref):
     """BASELINE config 1: single random 2^20-entry MLE, D=1, prove + verify, bit-exact vs the CPU oracle."""
     n = 20

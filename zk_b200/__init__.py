@@ -311,6 +311,22 @@ class SumcheckProof:
         self._round_polys_mont = round_polys_mont
         self._sum_mont = sum_mont
 
+    def to_bytes(self, challenges: Optional[Sequence[int]] = None, final_evals: Optional[Sequence[int]] = None) -> bytes:
+        """Proof dump: BE32(sum) || round polynomials || challenges || final evaluations."""
+        rp = np.ascontiguousarray(self._round_polys_mont)
+        n = rp.shape[0]
+        d1 = rp.shape[1] if rp.ndim == 3 else 1
+        ch = to_mont(self.field, list(challenges)) if challenges is not None and len(challenges) else None
+        fe = to_mont(self.field, list(final_evals)) if final_evals is not None and len(final_evals) else None
+        ln = C.c_size_t(0)
+        args = (self.field, self._sum_mont.ctypes.data, rp.ctypes.data if rp.size else None, n, d1 - 1,
+                ch.ctypes.data if ch is not None else None, fe.ctypes.data if fe is not None else None,
+                fe.shape[0] if fe is not None else 0)
+        _check(lib().zk_sumcheck_proof_dump(*args, None, 0, C.byref(ln), None))
+        out = np.zeros(ln.value, dtype=np.uint8)
+        _check(lib().zk_sumcheck_proof_dump(*args, out.ctypes.data, ln.value, C.byref(ln), None))
+        return out.tobytes()
+
     @classmethod
     def from_values(cls, field: int, sum_: int, round_polys: List[List[int]]):
         d1 = len(round_polys[0]) if round_polys else 1

@@ -68,6 +68,7 @@ SIGNATURES = {
     "zk_sumcheck_prove_host": (C.c_int, [vp, C.c_int, vpp, C.c_uint, C.c_uint, C.c_uint, vp, C.c_int, vp, vp, vp, vp]),
     "zk_sumcheck_verify": (C.c_int, [vp, vpp, C.c_uint, vp, vp, C.c_uint, C.c_uint]),
     "zk_sumcheck_verify_partial": (C.c_int, [C.c_int, vp, vp, C.c_uint, C.c_uint, vp, vp]),
+    "zk_sumcheck_proof_dump": (C.c_int, [C.c_int, vp, vp, C.c_uint, C.c_uint, vp, vp, C.c_uint, vp, C.c_size_t, C.POINTER(C.c_size_t), vp]),
     "zk_transcript_new": (vp, []),
     "zk_transcript_free": (None, [vp]),
     "zk_transcript_append": (None, [vp, C.c_char_p, C.c_size_t]),

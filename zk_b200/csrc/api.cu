@@ -996,6 +996,25 @@ int zk_sumcheck_verify(zk_ctx* ctx, const zk_table* const* tables, unsigned m, c
     return ZK_OK;
 }
 
+int zk_sumcheck_proof_dump(int field, const uint64_t sum[4], const uint64_t* round_polys, unsigned n_rounds,
+                           unsigned degree, const uint64_t* challenges, const uint64_t* final_evals, unsigned m,
+                           uint8_t* out, size_t out_cap, size_t* out_len, uint8_t digest_out[32]) {
+    if (!valid_field(field) || !sum || (n_rounds && !round_polys) || !out_len) return ZK_ERR_INVALID_ARG;
+    const size_t n_elems = 1 + (size_t)n_rounds * (degree + 1) + (challenges ? n_rounds : 0) + (final_evals ? m : 0);
+    *out_len = n_elems * 32;
+    if (!out) return ZK_OK;
+    if (out_cap < *out_len) return ZK_ERR_INVALID_ARG;
+    Field F(field);
+    uint8_t* w = out;
+    auto put = [&](const uint64_t* e) { F.to_be32(el_from(e), w); w += 32; };
+    put(sum);
+    for (size_t i = 0; i < (size_t)n_rounds * (degree + 1); i++) put(round_polys + 4 * i);
+    if (challenges) for (unsigned i = 0; i < n_rounds; i++) put(challenges + 4 * (size_t)i);
+    if (final_evals) for (unsigned k = 0; k < m; k++) put(final_evals + 4 * (size_t)k);
+    if (digest_out) zk_keccak256(out, *out_len, digest_out);
+    return ZK_OK;
+}
+
 // ---- transcript -------------------------------------------------------------------------------------
 zk_transcript* zk_transcript_new(void) { return new (std::nothrow) zk_transcript(); }
 void zk_transcript_free(zk_transcript* t) { delete t; }
