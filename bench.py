@@ -86,6 +86,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(n, m, d, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch, from the committed `ncu --set full`
+    capture of this exact workload (profiles/); None for any other configuration."""
+    if not (n - (world.bit_length() - 1) == 26 and m == 3 and d == 3):
+        return None, None
+    path = os.path.join(ROOT, "profiles", "r01_round_kernel_fold_D3_m3_n26_ncu_full.txt")
+    try:
+        vals = {}
+        for line in open(path):
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                if line.startswith(key + " ["):
+                    unit = line.split("[")[1].split("]")[0]
+                    v = float(line.split("=")[1].strip().replace(",", ""))
+                    vals[key] = v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+        return vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"], os.path.relpath(path, ROOT)
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -317,9 +336,10 @@ def run_ours(args):
     wide_per_item = 2 * m * 76 + prod_wide
     wide_per_s = wide_per_item * (local_n0 // 4) / fused_s
     mb = ctx.microbench(FIELD) if not args.no_microbench else {"fe_mul_per_s": float("nan"), "imad_wide_per_s": float("nan")}
+    traffic, traffic_src = ncu_traffic(n, m, d, world)
     roofline = {"bound": "hbm", "kernel": f"round_kernel<Fr381,{d},FOLD=true> (first fused fold+round-sum step, m={m})", "achieved": achieved,
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_src,
-                "traffic": None, "algorithmic_bytes_per_launch": fused_bytes, "launch_ms": fused_s * 1e3,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": fused_bytes, "launch_ms": fused_s * 1e3,
                 "int_pipe": {"bound": "IMAD.WIDE.U32 issue rate (half-rate integer multiply pipe)", "imad_wide_per_item": wide_per_item,
                              "achieved_imad_wide_per_s": wide_per_s, "peak_imad_wide_per_s": mb["imad_wide_per_s"],
                              "frac": wide_per_s / mb["imad_wide_per_s"], "field_mul_per_s": fused_muls / fused_s,
