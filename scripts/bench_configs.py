@@ -70,6 +70,37 @@ def run(name, n, m, d, absorb, verify=False):
     print(json.dumps(out), flush=True)
 
 
+def run_evaluate(n):
+    """The reference's own criterion bench (polynomial/benches/polynomial_evaluation.rs:85-105):
+    MultiLinearPolynomial::evaluate at n = 18..21 variables."""
+    t = zk.MultiLinearPolynomial.generate(n, 0, seed=SEED, ctx=ctx)
+    pt = zk.to_mont(0, [3 + 7 * i for i in range(n)])
+    out = np.zeros(4, dtype=np.uint64)
+
+    def ev():
+        ctx.check(lib.zk_mle_evaluate(ctx.h, t._h, pt.ctypes.data, n, out.ctypes.data))
+
+    ms, _ = timed(ev, reps=7, warm=2)
+    res = {"config": f"MultiLinearPolynomial::evaluate, {n} vars (reference criterion bench evaluate_{n}_vars)", "log_n": n,
+           "evaluate_ms": ms, "field_mul_per_s": ((1 << n) - 1) / (ms * 1e-3)}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import time
+
+        import cref
+
+        ref = cref.gen_table(0, SEED, 0, n)
+        t0 = time.perf_counter()
+        exp = cref.partial_evaluate(0, ref, n, 0, pt)
+        res["cpu_port_ms"] = (time.perf_counter() - t0) * 1e3
+        res["bit_exact_vs_cpu"] = bool((exp[0] == out).all())
+    except Exception as e:  # the oracle is only the checker here
+        res["cpu_port_ms"] = None
+    print(json.dumps(res), flush=True)
+
+
+for nv in (18, 19, 20, 21):
+    run_evaluate(nv)
 run("C1 single MLE 2^20, prove+verify", 20, 1, 1, True, verify=True)
 run("C1 shape, prove_partial", 20, 1, 1, False)
 run("C2 product of 2 MLEs 2^24, prove (with absorb)", 24, 2, 2, True)

@@ -77,6 +77,8 @@ struct zk_ctx {
     unsigned cur_seq = 0;                 // sequence number of the reduction in flight
     Fe* gather_buf = nullptr;             // persistent staging for the residual all-gather (grow-only)
     size_t gather_cap = 0;                // elements
+    Fe* eval_buf = nullptr;               // persistent half-size work table of zk_mle_evaluate (grow-only)
+    size_t eval_cap = 0;                  // elements
 };
 
 struct zk_table {
@@ -320,6 +322,7 @@ void zk_ctx_destroy(zk_ctx* c) {
     if (c->comm) nccl().CommDestroy(c->comm);
     for (auto* pl : c->ntt_plans) zk::ntt_plan_destroy(pl);
     cudaFree(c->gather_buf);
+    cudaFree(c->eval_buf);
     for (auto ev : c->events) cudaEventDestroy(ev);
     cudaFree(c->scratch.block_partials);
     cudaFree(c->scratch.ticket);
@@ -508,24 +511,37 @@ int zk_mle_evaluate(zk_ctx* ctx, const zk_table* in, const uint64_t* point, unsi
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         return ZK_OK;
     }
-    // first fold out of place into a half-size buffer, the rest in place (the reference folds inside
-    // its private clone, evaluation_form.rs:49-72)
-    zk_table* w = nullptr;
-    int st = table_alloc(ctx, in->field, in->n_vars - 1, in->local_len / 2, &w);
-    if (st != ZK_OK) return st;
-    cudaError_t e = zk::launch_fold_var(in->field, in->data, w->data, in->n_vars, 0, fe_from_u64x4(point), ctx->stream,
+    // first fold out of place into a half-size work buffer, the rest in place (the reference folds inside its
+    // private clone, evaluation_form.rs:49-72).  The buffer is kept by the context: a cudaMalloc/cudaFree pair
+    // costs more than all the folds of a 2^20-entry table.  All launches are queued back to back (the
+    // assignments are known up front); one synchronisation at the end.
+    const uint64_t half = in->local_len / 2;
+    if (ctx->eval_cap < half) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->eval_buf);
+        ctx->eval_buf = nullptr;
+        ctx->eval_cap = 0;
+        CU(ctx, cudaMalloc((void**)&ctx->eval_buf, (size_t)half * sizeof(Fe)));
+        ctx->eval_cap = half;
+    }
+    Fe* w = ctx->eval_buf;
+    cudaError_t e = zk::launch_fold_var(in->field, in->data, w, in->n_vars, 0, fe_from_u64x4(point), ctx->stream,
                                         &ctx->launches);
     zk::TablePtrs p{};
-    p.t[0] = w->data;
-    uint64_t cur = w->local_len;
+    p.t[0] = w;
+    uint64_t cur = half;
     for (unsigned s = 1; s < len && e == cudaSuccess; s++) {
         e = zk::launch_fold(in->field, p, 1, cur / 2, fe_from_u64x4(point + 4 * (size_t)s), ctx->stream, &ctx->launches);
         cur /= 2;
     }
     count(ctx);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out, w->data, 32, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, w, 32, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    zk_table_free(w);
+    if (ctx->eval_cap * sizeof(Fe) > ((size_t)1 << 30)) {  // do not hoard more than 1 GiB between calls
+        cudaFree(ctx->eval_buf);
+        ctx->eval_buf = nullptr;
+        ctx->eval_cap = 0;
+    }
     if (e != cudaSuccess) return cuda_fail(ctx, e, "evaluate");
     return ZK_OK;
 }
