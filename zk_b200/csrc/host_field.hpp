@@ -161,5 +161,21 @@ inline void fixed_mul_table(const Field& F, const El& r_mont, uint32_t out[8][8]
     }
 }
 
+// Multiples of a launch-wide multiplier for the device's fe_mul_fixed_f64 (field_f64.cuh):
+// out[i][j] = limb j (32 bits, as a double) of r * 2^(16 i + 32) mod p, canonical.  `r_mont` is r in Montgomery form.
+inline void fixed_mul_table_f64(const Field& F, const El& r_mont, double out[16][8]) {
+    const El two16 = F.from_u64((uint64_t)1 << 16);
+    El cur = F.mul(r_mont, F.from_u64((uint64_t)1 << 32));
+    for (int i = 0; i < 16; i++) {
+        uint64_t c[4];
+        F.to_canonical(cur, c);
+        for (int j = 0; j < 4; j++) {
+            out[i][2 * j] = (double)(uint32_t)c[j];
+            out[i][2 * j + 1] = (double)(uint32_t)(c[j] >> 32);
+        }
+        cur = F.mul(cur, two16);
+    }
+}
+
 }  // namespace host
 }  // namespace zk

@@ -17,7 +17,10 @@
 // global memory -> the last block to finish (atomic ticket) folds the partials and publishes the
 // D+1 evaluations to device memory and to mapped pinned host memory.
 #include "kernels.h"
+#include "field_f64.cuh"
 #include "host_field.hpp"
+
+#include <cstdlib>
 
 namespace zk {
 namespace {
@@ -25,6 +28,10 @@ namespace {
 constexpr int kThreads = 128;
 
 constexpr int kWarps = kThreads / 32;
+
+struct FixedMulF64Sel {
+    FixedMulF64 t[2];  // two identical copies, see `ksel` in round_kernel
+};
 
 __device__ __forceinline__ Fe ld_fe_cg(const Fe* p) {  // L2-coherent load (other blocks' partials)
     Fe r;
@@ -218,9 +225,14 @@ __device__ __forceinline__ Fe accw_reduce(const uint4* a) {
 // instead of (0, 1, 2, 3).  After the second factor the running product is a quadratic, fixed by three
 // values, so its value at -1 is 2(A(0) + A(inf)) - A(1): one multiplication less per item (7 instead of 8).
 // The four sums are mapped back to S(0..3) by exact field arithmetic in the last block (toom_to_evals).
-template <class F, int D, bool FOLD, bool TOOM = false>
+// F64 (only with FOLD): the folds run on the FP64 pipe (field_f64.cuh: exact DFMA dot products against 16 host-made
+// multiples of the challenge, one Montgomery row) instead of fe_mul_fixed's 76 wide multiplies, so the two pipes
+// share the item: the product multiplications keep the integer-multiply pipe, the folds the FP64 pipe.
+template <class F, int D, bool FOLD, bool TOOM = false, bool F64 = false>
 __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
-    round_kernel(TablePtrs tabs, int m, uint64_t q, const __grid_constant__ FixedMul rtab, ReduceArgs ra) {
+    round_kernel(TablePtrs tabs, int m, uint64_t q, const __grid_constant__ FixedMul rtab,
+                 const __grid_constant__ FixedMulF64Sel rtab64, ReduceArgs ra) {
+    static_assert(!F64 || FOLD, "the FP64 variant only changes the folds");
     static_assert(!TOOM || D == 3, "the Toom point set is wired for cubics");
     extern __shared__ uint4 accw_all[];  // [(D+1)][5][kThreads]
     __shared__ Fe* s_tab[kMaxFactors];
@@ -257,15 +269,24 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
         for (int k = 0; k < m; k++) {
             Fe* T = s_tab[k];
             Fe lo, hi;
+            // Always 0 — but a loop-variant index in ptxas's eyes: with a loop-invariant address it hoists all 128
+            // table entries out of the loop, runs out of uniform registers and spills them to local memory.
+            const int ksel = F64 ? (k >> 16) : 0;
             const bool more_k = (k + 1 < m);
             const uint64_t nj = more_k ? j : j + stride;
             Fe* NT = s_tab[more_k ? k + 1 : 0];
             if (FOLD) {  // T has 4q entries: fold (j, j+2q) and (j+q, j+3q) at r, write back to j and j+q
                 if (kFoldPrefetch) {
-                    lo = fe_fold_fixed<F>(n0, n2, rtab);  // the challenge enters as precomputed multiples (fe_mul_fixed)
-                    st_fe(T + j, lo);
-                    hi = fe_fold_fixed<F>(n1, n3, rtab);
-                    st_fe(T + j + q, hi);
+                    if (F64) {
+                        fe_fold_fixed_f64_x2<F>(lo, hi, n0, n1, n2, n3, rtab64.t[ksel]);
+                        st_fe(T + j, lo);
+                        st_fe(T + j + q, hi);
+                    } else {
+                        lo = fe_fold_fixed<F>(n0, n2, rtab);  // the challenge enters as precomputed multiples (fe_mul_fixed)
+                        st_fe(T + j, lo);
+                        hi = fe_fold_fixed<F>(n1, n3, rtab);
+                        st_fe(T + j + q, hi);
+                    }
                     if (nj < q) {
                         n0 = ld_fe_stream(NT + nj); n2 = ld_fe_stream(NT + nj + 2 * q);
                         n1 = ld_fe_stream(NT + nj + q); n3 = ld_fe_stream(NT + nj + 3 * q);
@@ -273,10 +294,16 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
                 } else {
                     Fe x0 = ld_fe_stream(T + j), x2 = ld_fe_stream(T + j + 2 * q);
                     Fe x1 = ld_fe_stream(T + j + q), x3 = ld_fe_stream(T + j + 3 * q);
-                    lo = fe_fold_fixed<F>(x0, x2, rtab);
-                    st_fe(T + j, lo);
-                    hi = fe_fold_fixed<F>(x1, x3, rtab);
-                    st_fe(T + j + q, hi);
+                    if (F64) {
+                        fe_fold_fixed_f64_x2<F>(lo, hi, x0, x1, x2, x3, rtab64.t[ksel]);
+                        st_fe(T + j, lo);
+                        st_fe(T + j + q, hi);
+                    } else {
+                        lo = fe_fold_fixed<F>(x0, x2, rtab);
+                        st_fe(T + j, lo);
+                        hi = fe_fold_fixed<F>(x1, x3, rtab);
+                        st_fe(T + j + q, hi);
+                    }
                 }
             } else {  // T has 2q entries: the pair is (j, j+q)
                 lo = n0;
@@ -418,18 +445,44 @@ FixedMul make_fixed(const Fe& r) {
     return t;
 }
 
-template <class F, int D, bool FOLD, bool TOOM = false>
-cudaError_t do_round(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st) {
+template <class F>
+FixedMulF64Sel make_fixed_f64(const Fe& r) {
+    host::Field HF(F::ID);
+    host::El rm;
+    std::memcpy(rm.v, r.v, 32);
+    FixedMulF64Sel t;
+    host::fixed_mul_table_f64(HF, rm, t.t[0].t);
+    t.t[1] = t.t[0];
+    return t;
+}
+
+// ZK_B200_FOLD_PIPE=f64 selects the FP64-pipe folds (field_f64.cuh) for A/B measurements; default: integer pipe.
+inline bool fold_on_f64() {
+    static const bool on = [] {
+        const char* e = std::getenv("ZK_B200_FOLD_PIPE");
+        return e && e[0] == 'f';
+    }();
+    return on;
+}
+
+template <class F, int D, bool FOLD, bool TOOM, bool F64>
+cudaError_t do_round_v(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st) {
     constexpr size_t smem = (size_t)(D + 1) * 5 * kThreads * sizeof(uint4);
     static int bpsm = [] {
-        cudaFuncSetAttribute(round_kernel<F, D, FOLD, TOOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(round_kernel<F, D, FOLD, TOOM, F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<F, D, FOLD, TOOM>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<F, D, FOLD, TOOM, F64>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
         return nb;
     }();
     unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
-    round_kernel<F, D, FOLD, TOOM><<<grid, kThreads, smem, st>>>(tabs, m, q, make_fixed<F>(r), make_ra(s, 0));
+    round_kernel<F, D, FOLD, TOOM, F64><<<grid, kThreads, smem, st>>>(
+        tabs, m, q, (FOLD && !F64) ? make_fixed<F>(r) : FixedMul{}, F64 ? make_fixed_f64<F>(r) : FixedMulF64Sel{}, make_ra(s, 0));
     return cudaGetLastError();
+}
+template <class F, int D, bool FOLD, bool TOOM = false>
+cudaError_t do_round(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st) {
+    if (FOLD && fold_on_f64()) return do_round_v<F, D, FOLD, TOOM, FOLD>(tabs, m, q, r, s, st);
+    return do_round_v<F, D, FOLD, TOOM, false>(tabs, m, q, r, s, st);
 }
 template <class F, bool FOLD>
 cudaError_t do_round_deg(const TablePtrs& tabs, int m, int degree, uint64_t q, const Fe& r, const ReduceScratch& s,
