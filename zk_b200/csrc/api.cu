@@ -233,8 +233,9 @@ int ctx_init(zk_ctx* c) {
     c->scratch.num_sms = prop.multiProcessorCount;
     const size_t np = (size_t)zk::kMaxGridBlocks * (zk::kMaxDegree + 1);
     CU(c, cudaMalloc((void**)&c->scratch.block_partials, np * sizeof(Fe)));
-    CU(c, cudaMalloc((void**)&c->scratch.ticket, sizeof(unsigned)));
-    CU(c, cudaMemset(c->scratch.ticket, 0, sizeof(unsigned)));
+    // ticket word + (128 bytes further) the 64-bit work counter of the round kernels
+    CU(c, cudaMalloc((void**)&c->scratch.ticket, 256));
+    CU(c, cudaMemset(c->scratch.ticket, 0, 256));
     CU(c, cudaMalloc((void**)&c->scratch.result_dev, (zk::kMaxDegree + 1) * sizeof(Fe)));
     CU(c, cudaHostAlloc((void**)&c->scratch.result_host, (zk::kMaxDegree + 1) * sizeof(Fe), cudaHostAllocMapped));
     CU(c, cudaHostGetDevicePointer((void**)&c->scratch.result_host_devptr, c->scratch.result_host, 0));

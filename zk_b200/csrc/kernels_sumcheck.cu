@@ -25,6 +25,16 @@
 namespace zk {
 namespace {
 
+// tuning knobs (resident blocks per SM the register allocator must allow, per degree)
+#ifndef ZK_RK_MINBLOCKS_D1
+#define ZK_RK_MINBLOCKS_D1 6
+#endif
+#ifndef ZK_RK_MINBLOCKS_D2
+#define ZK_RK_MINBLOCKS_D2 5
+#endif
+#ifndef ZK_RK_MINBLOCKS_D3
+#define ZK_RK_MINBLOCKS_D3 4
+#endif
 constexpr int kThreads = 128;
 
 constexpr int kWarps = kThreads / 32;
@@ -65,7 +75,10 @@ struct ReduceArgs {
     unsigned* flag_host;  // mapped pinned word the host spins on (saves a stream synchronisation per round)
     unsigned seq;
     uint64_t* lanes;      // sharded runs: one 32-bit limb per u64 lane, the input of the exact ncclSum all-reduce
+    int dynamic;          // round kernels: chunks from the global work counter (WarpChunks) instead of a static split
+    int group_log2;       // round kernels: a warp takes 2^group_log2 consecutive chunks per request
 };
+constexpr int kWorkCounterOffset = 32;  // the work counter lives 128 bytes after the ticket (own cache line)
 
 // Block-level reduction of NP per-thread accumulators, then grid-level via last-block-done.
 // x / 2 in the field (works on any residue representation): (x + (x odd ? p : 0)) >> 1
@@ -163,6 +176,7 @@ __device__ __forceinline__ void reduce_publish(Fe* acc, const ReduceArgs& ra) {
             }
         }
         *ra.ticket = 0;  // ready for the next launch on this stream
+        ra.ticket[kWorkCounterOffset] = 0;
         __threadfence_system();
         if (ra.seq != 0) {
             *(volatile unsigned*)ra.flag_host = ra.seq;
@@ -172,52 +186,67 @@ __device__ __forceinline__ void reduce_publish(Fe* acc, const ReduceArgs& ra) {
 }
 
 // ---- wide (17-word) per-thread accumulators in shared memory -------------------------------------------
-// Layout: uint4 accw[t][5][kThreads]; words 0..15 = the unreduced sum, word 16 = overflow count.
-__device__ __forceinline__ void accw_zero(uint4* accw, int np) {
-    for (int i = threadIdx.x; i < np * 5 * kThreads; i += kThreads) accw[i] = make_uint4(0, 0, 0, 0);
+// Layout per evaluation point t: uint4 q[4][kThreads] (words 0..15 = the unreduced sum) and uint32_t ov[kThreads]
+// (word 16 = overflow count).  An Accw points at this thread's column of point 0; point t is `at(t, D+1)`.
+struct Accw {
+    uint4* q;       // + g * kThreads, g = 0..3
+    uint32_t* ov;
+};
+__host__ __device__ constexpr size_t accw_bytes(int np) { return (size_t)np * (4 * sizeof(uint4) + sizeof(uint32_t)) * kThreads; }
+__device__ __forceinline__ Accw accw_base(uint4* smem, int np) {
+    return Accw{smem + threadIdx.x, reinterpret_cast<uint32_t*>(smem + (size_t)np * 4 * kThreads) + threadIdx.x};
+}
+__device__ __forceinline__ Accw accw_at(const Accw& a, int t) { return Accw{a.q + t * 4 * kThreads, a.ov + t * kThreads}; }
+__device__ __forceinline__ void accw_zero(uint4* smem, int np) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(smem);
+    for (int i = threadIdx.x; i < (int)(accw_bytes(np) / 4); i += kThreads) w[i] = 0;
 }
 // acc += w[0..15]  (one 17-word carry chain)
-__device__ __forceinline__ void accw_add16(uint4* a, const uint32_t* w) {
-    uint4 q0 = a[0 * kThreads], q1 = a[1 * kThreads], q2 = a[2 * kThreads], q3 = a[3 * kThreads], q4 = a[4 * kThreads];
+__device__ __forceinline__ void accw_add16(const Accw& a, const uint32_t* w) {
+    uint4 q0 = a.q[0 * kThreads], q1 = a.q[1 * kThreads], q2 = a.q[2 * kThreads], q3 = a.q[3 * kThreads];
+    uint32_t ov = a.ov[0];
     asm("add.cc.u32 %0,%0,%17;\n\taddc.cc.u32 %1,%1,%18;\n\taddc.cc.u32 %2,%2,%19;\n\taddc.cc.u32 %3,%3,%20;\n\t"
         "addc.cc.u32 %4,%4,%21;\n\taddc.cc.u32 %5,%5,%22;\n\taddc.cc.u32 %6,%6,%23;\n\taddc.cc.u32 %7,%7,%24;\n\t"
         "addc.cc.u32 %8,%8,%25;\n\taddc.cc.u32 %9,%9,%26;\n\taddc.cc.u32 %10,%10,%27;\n\taddc.cc.u32 %11,%11,%28;\n\t"
         "addc.cc.u32 %12,%12,%29;\n\taddc.cc.u32 %13,%13,%30;\n\taddc.cc.u32 %14,%14,%31;\n\taddc.cc.u32 %15,%15,%32;\n\t"
         "addc.u32 %16,%16,0;"
         : "+r"(q0.x), "+r"(q0.y), "+r"(q0.z), "+r"(q0.w), "+r"(q1.x), "+r"(q1.y), "+r"(q1.z), "+r"(q1.w), "+r"(q2.x),
-          "+r"(q2.y), "+r"(q2.z), "+r"(q2.w), "+r"(q3.x), "+r"(q3.y), "+r"(q3.z), "+r"(q3.w), "+r"(q4.x)
+          "+r"(q2.y), "+r"(q2.z), "+r"(q2.w), "+r"(q3.x), "+r"(q3.y), "+r"(q3.z), "+r"(q3.w), "+r"(ov)
         : "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]), "r"(w[9]),
           "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]));
-    a[0 * kThreads] = q0; a[1 * kThreads] = q1; a[2 * kThreads] = q2; a[3 * kThreads] = q3; a[4 * kThreads] = q4;
+    a.q[0 * kThreads] = q0; a.q[1 * kThreads] = q1; a.q[2 * kThreads] = q2; a.q[3 * kThreads] = q3;
+    a.ov[0] = ov;
 }
 // acc += x * 2^256 (x a reduced element): what an ordinary product x*R contributes before the deferred reduction
-__device__ __forceinline__ void accw_add_hi(uint4* a, const Fe& x) {
-    uint4 q2 = a[2 * kThreads], q3 = a[3 * kThreads], q4 = a[4 * kThreads];
+__device__ __forceinline__ void accw_add_hi(const Accw& a, const Fe& x) {
+    uint4 q2 = a.q[2 * kThreads], q3 = a.q[3 * kThreads];
+    uint32_t ov = a.ov[0];
     asm("add.cc.u32 %0,%0,%9;\n\taddc.cc.u32 %1,%1,%10;\n\taddc.cc.u32 %2,%2,%11;\n\taddc.cc.u32 %3,%3,%12;\n\t"
         "addc.cc.u32 %4,%4,%13;\n\taddc.cc.u32 %5,%5,%14;\n\taddc.cc.u32 %6,%6,%15;\n\taddc.cc.u32 %7,%7,%16;\n\t"
         "addc.u32 %8,%8,0;"
-        : "+r"(q2.x), "+r"(q2.y), "+r"(q2.z), "+r"(q2.w), "+r"(q3.x), "+r"(q3.y), "+r"(q3.z), "+r"(q3.w), "+r"(q4.x)
+        : "+r"(q2.x), "+r"(q2.y), "+r"(q2.z), "+r"(q2.w), "+r"(q3.x), "+r"(q3.y), "+r"(q3.z), "+r"(q3.w), "+r"(ov)
         : "r"(x.v[0]), "r"(x.v[1]), "r"(x.v[2]), "r"(x.v[3]), "r"(x.v[4]), "r"(x.v[5]), "r"(x.v[6]), "r"(x.v[7]));
-    a[2 * kThreads] = q2; a[3 * kThreads] = q3; a[4 * kThreads] = q4;
+    a.q[2 * kThreads] = q2; a.q[3 * kThreads] = q3;
+    a.ov[0] = ov;
 }
 template <class F>
-__device__ __forceinline__ Fe accw_reduce(const uint4* a) {
+__device__ __forceinline__ Fe accw_reduce(const Accw& a) {
     uint32_t v[17];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        uint4 q = a[i * kThreads];
+        uint4 q = a.q[i * kThreads];
         v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
     }
-    v[16] = a[4 * kThreads].x;
+    v[16] = a.ov[0];
     return fe_redc_wide<F>(v);
 }
 
-// One hypercube item, all factors: lo_k / hi_k are the pair values of factor k for this item (after the
+// One hypercube item, factor k of m: lo / hi are the pair values of this factor for the item (after the
 // optional fold).  Term t of the round polynomial is prod_k e_k(t), e_k(0) = lo_k, e_k(1) = hi_k,
 // e_k(t+1) = e_k(t) + (hi_k - lo_k)  (prover.rs:49-56 evaluates at t = 0..D by a full partial_evaluate +
 // prod_reduce each; the values are the same field elements).  Factors are visited sequentially so that only
-// the D+1 running products and one factor's pair are live (128 registers, 4 blocks per SM), and `m` is a
-// run-time value: one instantiation per degree serves every factor count.
+// the D+1 running products and one factor's pair are live, and `m` is a run-time value: one instantiation per
+// degree serves every factor count.
 // The LAST multiplication of every term is not reduced: the 512-bit product is added to a 17-word
 // per-thread accumulator in shared memory and Montgomery-reduced once per thread at the end
 // (sum of products then one REDC == sum of REDCs, exactly, mod p): 64 instead of 112 wide multiplies.
@@ -225,33 +254,139 @@ __device__ __forceinline__ Fe accw_reduce(const uint4* a) {
 // instead of (0, 1, 2, 3).  After the second factor the running product is a quadratic, fixed by three
 // values, so its value at -1 is 2(A(0) + A(inf)) - A(1): one multiplication less per item (7 instead of 8).
 // The four sums are mapped back to S(0..3) by exact field arithmetic in the last block (toom_to_evals).
+template <class F, int D, bool TOOM>
+__device__ __forceinline__ void item_terms(int k, bool last, Fe lo, Fe hi, Fe* pr, const Accw& accw) {
+    if (TOOM) {  // pr[0..3] live at t = 0, 1, -1, inf ; m == 3
+        const Fe d = fe_sub<F>(hi, lo);
+        if (k == 0) {
+            pr[0] = lo; pr[1] = hi; pr[3] = d; pr[2] = fe_sub<F>(lo, d);
+        } else if (!last) {
+            pr[0] = fe_mul<F>(lo, pr[0]);
+            pr[1] = fe_mul<F>(hi, pr[1]);
+            pr[3] = fe_mul<F>(d, pr[3]);
+            const Fe s02 = fe_add<F>(pr[0], pr[3]);
+            pr[2] = fe_sub<F>(fe_add<F>(s02, s02), pr[1]);
+        } else {
+            uint32_t w[16];
+            fe_mul_wide(w, lo, pr[0]); accw_add16(accw, w);
+            fe_mul_wide(w, hi, pr[1]); accw_add16(accw_at(accw, 1), w);
+            fe_mul_wide(w, fe_sub<F>(lo, d), pr[2]); accw_add16(accw_at(accw, 2), w);
+            fe_mul_wide(w, d, pr[3]); accw_add16(accw_at(accw, 3), w);
+        }
+    } else if (k == 0) {
+        pr[0] = lo;
+        if (D >= 1) pr[1] = hi;
+        if (D >= 2) {
+            Fe d = fe_sub<F>(hi, lo);
+#pragma unroll
+            for (int t = 2; t <= D; t++) {
+                hi = fe_add<F>(hi, d);
+                pr[t] = hi;
+            }
+        }
+        if (last) {  // m == 1: the terms are the table values themselves
+#pragma unroll
+            for (int t = 0; t <= D; t++) accw_add_hi(accw_at(accw, t), pr[t]);
+        }
+    } else {
+        uint32_t w[16];
+        if (last) { fe_mul_wide(w, lo, pr[0]); accw_add16(accw, w); } else pr[0] = fe_mul<F>(lo, pr[0]);
+        if (D >= 2) lo = fe_sub<F>(hi, lo);  // lo := d
+        if (D >= 1) {
+            if (last) { fe_mul_wide(w, hi, pr[1]); accw_add16(accw_at(accw, 1), w); } else pr[1] = fe_mul<F>(hi, pr[1]);
+        }
+#pragma unroll
+        for (int t = 2; t <= D; t++) {
+            hi = fe_add<F>(hi, lo);
+            if (last) { fe_mul_wide(w, hi, pr[t]); accw_add16(accw_at(accw, t), w); } else pr[t] = fe_mul<F>(hi, pr[t]);
+        }
+    }
+}
+
+// the two folds of one fused-round item: lo = fold(x0, x2), hi = fold(x1, x3) at the launch-wide challenge
+template <class F, bool F64>
+__device__ __forceinline__ void fold_pair(Fe& lo, Fe& hi, const Fe& x0, const Fe& x1, const Fe& x2, const Fe& x3,
+                                          const FixedMul& rtab, const FixedMulF64& rtab64) {
+    if (F64) {
+        fe_fold_fixed_f64_x2<F>(lo, hi, x0, x1, x2, x3, rtab64);
+    } else {
+        lo = fe_fold_fixed<F>(x0, x2, rtab);  // the challenge enters as precomputed multiples (fe_mul_fixed)
+        hi = fe_fold_fixed<F>(x1, x3, rtab);
+    }
+}
+
+// ---- work distribution ------------------------------------------------------------------------------------------
+// The unit of work is a chunk of 32 consecutive items (one warp iteration).  A static grid-stride split leaves
+// ~20 % of the warp slots empty on average (ncu: 3.1-3.2 of 4 warps active per scheduler, uniformly on every
+// SM): the schedulers favour some warps, those finish their share early and the rest run out the kernel at low
+// occupancy.  So each warp takes its first two chunks statically and every later one from a global counter
+// (one atomicAdd per 32 items, requested a whole chunk ahead so its latency is hidden); the last block resets
+// the counter together with the ticket.  ra.dynamic == 0 keeps the static split (A/B measurements).
+template <bool GROUPED>  // GROUPED = false: one chunk per request (three-factor items), two registers less
+struct WarpChunks {      // 32-bit chunk ids: tables of up to 2^37 items
+    uint32_t c, cn;           // current chunk, next chunk
+    uint32_t gn;              // GROUPED: the group after the one `c` is in
+    uint32_t fetched;
+    __device__ __forceinline__ WarpChunks(const ReduceArgs& ra, int warp) {
+        const uint32_t tw = gridDim.x * kWarps, wid = blockIdx.x * kWarps + warp;
+        if (GROUPED) {
+            c = wid << ra.group_log2;
+            gn = wid + tw;
+            cn = ra.group_log2 ? c + 1 : gn;
+        } else {
+            c = wid;
+            cn = wid + tw;
+        }
+        fetched = 0;
+    }
+    __device__ __forceinline__ static bool live(uint32_t chunk, uint64_t q) { return (uint64_t)chunk * 32 < q; }
+    // top of a chunk: at the first chunk of a group ask for the group after next
+    __device__ __forceinline__ void request(const ReduceArgs& ra, int lane) {
+        const uint32_t gmask = GROUPED ? (1u << ra.group_log2) - 1u : 0u;
+        if (ra.dynamic && lane == 0 && (c & gmask) == 0) fetched = atomicAdd(ra.ticket + kWorkCounterOffset, 1u);
+    }
+    // bottom of a chunk (all lanes converged)
+    __device__ __forceinline__ void advance(const ReduceArgs& ra) {
+        const uint32_t tw = gridDim.x * kWarps;
+        if (GROUPED) {
+            const uint32_t gmask = (1u << ra.group_log2) - 1u;
+            if (((c + 1) & gmask) == 0)  // `c` was the last chunk of its group (warp-uniform)
+                gn = ra.dynamic ? __shfl_sync(0xffffffffu, fetched, 0) + 2 * tw : gn + tw;
+            c = cn;
+            cn = ((c + 1) & gmask) ? c + 1 : gn << ra.group_log2;
+        } else {
+            const uint32_t cnn = ra.dynamic ? __shfl_sync(0xffffffffu, fetched, 0) + 2 * tw : cn + tw;
+            c = cn;
+            cn = cnn;
+        }
+    }
+};
+
+// ---- register-prefetch variant (any q; the only variant for q < 32) -----------------------------------------
 // F64 (only with FOLD): the folds run on the FP64 pipe (field_f64.cuh: exact DFMA dot products against 16 host-made
-// multiples of the challenge, one Montgomery row) instead of fe_mul_fixed's 76 wide multiplies, so the two pipes
-// share the item: the product multiplications keep the integer-multiply pipe, the folds the FP64 pipe.
+// multiples of the challenge, one Montgomery row) instead of fe_mul_fixed's 76 wide multiplies.
 template <class F, int D, bool FOLD, bool TOOM = false, bool F64 = false>
-__global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
+__global__ void __launch_bounds__(kThreads, (D <= 1) ? ZK_RK_MINBLOCKS_D1 : (D == 2 ? ZK_RK_MINBLOCKS_D2 : ZK_RK_MINBLOCKS_D3))
     round_kernel(TablePtrs tabs, int m, uint64_t q, const __grid_constant__ FixedMul rtab,
                  const __grid_constant__ FixedMulF64Sel rtab64, ReduceArgs ra) {
-    static_assert(!F64 || FOLD, "the FP64 variant only changes the folds");
     static_assert(!TOOM || D == 3, "the Toom point set is wired for cubics");
-    extern __shared__ uint4 accw_all[];  // [(D+1)][5][kThreads]
+    static_assert(!F64 || FOLD, "the FP64 variant only changes the folds");
+    extern __shared__ uint4 accw_all[];  // accw_bytes(D+1)
     __shared__ Fe* s_tab[kMaxFactors];
     if (threadIdx.x < kMaxFactors) s_tab[threadIdx.x] = tabs.t[threadIdx.x];
     accw_zero(accw_all, D + 1);
     __syncthreads();
-    uint4* accw = accw_all + threadIdx.x;  // + t * 5 * kThreads + word_group * kThreads
-    const uint64_t stride = (uint64_t)gridDim.x * kThreads;
-    const uint64_t j0 = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-    // Round 0 (no fold) software-pipelines its loads: the pair of the next (item, factor) is in flight while this
-    // one is multiplied (+6 % on that kernel).  The fused kernel does not: the four extra elements cost 32
-    // registers and measured slower.
+    const Accw accw = accw_base(accw_all, D + 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpChunks<!TOOM> wc(ra, warp);
     // Software pipelining of the global loads.  Round 0 (no fold) keeps the pair of the next (item, factor) in
     // flight while this one is multiplied.  The fused kernel issues the four loads of the next (item, factor)
     // right AFTER this factor's folds (when x0..x3 are dead) so they land during the product multiplications
     // (-4 % at D = 3; at D <= 2 the register budget of the higher-occupancy variants makes it a loss).
     constexpr bool kFoldPrefetch = FOLD && D >= 3;
     Fe n0, n1, n2, n3;
-    if (j0 < q) {
+    if ((uint64_t)wc.c * 32 + lane < q) {
+        const uint64_t j0 = (uint64_t)wc.c * 32 + lane;
         Fe* T = s_tab[0];
         if (FOLD) {
             if (kFoldPrefetch) {
@@ -263,107 +398,170 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? 6 : (D == 2 ? 5 : 4))
         }
     }
 #pragma unroll 1
-    for (uint64_t j = j0; j < q; j += stride) {
+    while (WarpChunks<!TOOM>::live(wc.c, q)) {
+        wc.request(ra, lane);
+        const uint64_t j = (uint64_t)wc.c * 32 + lane, jn = (uint64_t)wc.cn * 32 + lane;
+        const bool nvalid = jn < q;
+        if (j < q) {  // false only in the single ragged chunk of a table with fewer than 32 items
+            Fe pr[D + 1];
+#pragma unroll 1
+            for (int k = 0; k < m; k++) {
+                Fe* T = s_tab[k];
+                Fe lo, hi;
+                // Always 0 — but a loop-variant index in ptxas's eyes: with a loop-invariant address it hoists all 128
+                // table entries out of the loop, runs out of uniform registers and spills them to local memory.
+                const int ksel = F64 ? (k >> 16) : 0;
+                const bool more_k = (k + 1 < m);
+                const uint64_t nj = more_k ? j : jn;
+                const bool nok = more_k || nvalid;
+                Fe* NT = s_tab[more_k ? k + 1 : 0];
+                if (FOLD) {  // T has 4q entries: fold (j, j+2q) and (j+q, j+3q) at r, write back to j and j+q
+                    if (kFoldPrefetch) {
+                        fold_pair<F, F64>(lo, hi, n0, n1, n2, n3, rtab, rtab64.t[ksel]);
+                        st_fe(T + j, lo);
+                        st_fe(T + j + q, hi);
+                        if (nok) {
+                            n0 = ld_fe_stream(NT + nj); n2 = ld_fe_stream(NT + nj + 2 * q);
+                            n1 = ld_fe_stream(NT + nj + q); n3 = ld_fe_stream(NT + nj + 3 * q);
+                        }
+                    } else {
+                        Fe x0 = ld_fe_stream(T + j), x2 = ld_fe_stream(T + j + 2 * q);
+                        Fe x1 = ld_fe_stream(T + j + q), x3 = ld_fe_stream(T + j + 3 * q);
+                        fold_pair<F, F64>(lo, hi, x0, x1, x2, x3, rtab, rtab64.t[ksel]);
+                        st_fe(T + j, lo);
+                        st_fe(T + j + q, hi);
+                    }
+                } else {  // T has 2q entries: the pair is (j, j+q)
+                    lo = n0;
+                    hi = n1;
+                    if (nok) {
+                        n0 = ld_fe_stream(NT + nj);
+                        n1 = ld_fe_stream(NT + nj + q);
+                    }
+                }
+                item_terms<F, D, TOOM>(k, k == m - 1, lo, hi, pr, accw);
+            }
+        }
+        wc.advance(ra);
+    }
+    Fe acc[D + 1];
+#pragma unroll 1
+    for (int t = 0; t <= D; t++) acc[t] = accw_reduce<F>(accw_at(accw, t));
+    __syncthreads();
+    reduce_publish<F, D + 1, TOOM>(acc, ra);
+}
+
+// ---- TMA-staged variant (q a multiple of 32) ---------------------------------------------------------------
+// The register-prefetch kernel above keeps the next factor's four elements in 32 registers across the product
+// multiplications; at the 128-register cap ptxas spills part of them right after the load, and that spill store
+// waits out the full HBM latency (ncu: 7-14 % of all stall samples on one STL).  Here each warp owns a 4 KB slab
+// of shared memory and one mbarrier: lane 0 issues cp.async.bulk (TMA) copies of the warp's NS contiguous 1 KB
+// runs — T[jw .. jw+32) at offsets 0, q, 2q, 3q — for the NEXT (item, factor) as soon as the current one has been
+// read out of the slab, so a whole factor step (~4 us) hides the latency, no register is tied up by data in flight
+// and nothing is spilled.  Warp-private: no block-level barrier in the loop.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MBAR_DONE;\n\t"
+        "bra MBAR_WAIT;\n\t"
+        "MBAR_DONE:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ Fe lds_fe(const Fe* p) {
+    Fe r;
+    const uint32_t a = smem_u32(p);
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]) : "r"(a));
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "r"(a));
+    return r;
+}
+
+template <bool FOLD>
+__host__ __device__ constexpr size_t stage_bytes() { return (size_t)kWarps * (FOLD ? 4 : 2) * 32 * sizeof(Fe); }
+
+template <class F, int D, bool FOLD, bool TOOM = false, bool F64 = false>
+__global__ void __launch_bounds__(kThreads, (D <= 1) ? ZK_RK_MINBLOCKS_D1 : (D == 2 ? ZK_RK_MINBLOCKS_D2 : ZK_RK_MINBLOCKS_D3))
+    round_kernel_tma(TablePtrs tabs, int m, uint64_t q, const __grid_constant__ FixedMul rtab,
+                     const __grid_constant__ FixedMulF64Sel rtab64, ReduceArgs ra) {
+    static_assert(!TOOM || D == 3, "the Toom point set is wired for cubics");
+    static_assert(!F64 || FOLD, "the FP64 variant only changes the folds");
+    constexpr int NS = FOLD ? 4 : 2;  // contiguous runs per (warp, factor): offsets 0, q, (2q, 3q)
+    extern __shared__ uint4 smem_all[];  // accw_bytes(D+1) | stage_bytes<FOLD>()
+    __shared__ Fe* s_tab[kMaxFactors];
+    __shared__ __align__(8) unsigned long long s_bar[kWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < kMaxFactors) s_tab[threadIdx.x] = tabs.t[threadIdx.x];
+    accw_zero(smem_all, D + 1);
+    const uint32_t bar = smem_u32(&s_bar[warp]);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const Accw accw = accw_base(smem_all, D + 1);
+    Fe* slab = reinterpret_cast<Fe*>(reinterpret_cast<unsigned char*>(smem_all) + accw_bytes(D + 1)) + warp * NS * 32;
+    const uint32_t slab_u32 = smem_u32(slab);
+    WarpChunks<!TOOM> wc(ra, warp);  // q % 32 == 0: every chunk is a full 1 KB run in each stream
+    auto issue = [&](uint64_t jw, int k) {  // lane 0 only
+        const Fe* T = s_tab[k] + jw;
+        mbar_expect_tx(bar, NS * 32 * (uint32_t)sizeof(Fe));
+#pragma unroll
+        for (int s = 0; s < NS; s++) tma_load_1d(slab_u32 + s * 32 * (uint32_t)sizeof(Fe), T + s * q, 32 * (uint32_t)sizeof(Fe), bar);
+    };
+    if (WarpChunks<!TOOM>::live(wc.c, q) && lane == 0) issue((uint64_t)wc.c * 32, 0);
+    uint32_t parity = 0;
+#pragma unroll 1
+    while (WarpChunks<!TOOM>::live(wc.c, q)) {
+        wc.request(ra, lane);
+        const uint64_t jw = (uint64_t)wc.c * 32, j = jw + lane;
         Fe pr[D + 1];
 #pragma unroll 1
         for (int k = 0; k < m; k++) {
             Fe* T = s_tab[k];
+            const int ksel = F64 ? (k >> 16) : 0;  // always 0, see round_kernel
+            mbar_wait(bar, parity);
+            parity ^= 1;
             Fe lo, hi;
-            // Always 0 — but a loop-variant index in ptxas's eyes: with a loop-invariant address it hoists all 128
-            // table entries out of the loop, runs out of uniform registers and spills them to local memory.
-            const int ksel = F64 ? (k >> 16) : 0;
             const bool more_k = (k + 1 < m);
-            const uint64_t nj = more_k ? j : j + stride;
-            Fe* NT = s_tab[more_k ? k + 1 : 0];
-            if (FOLD) {  // T has 4q entries: fold (j, j+2q) and (j+q, j+3q) at r, write back to j and j+q
-                if (kFoldPrefetch) {
-                    if (F64) {
-                        fe_fold_fixed_f64_x2<F>(lo, hi, n0, n1, n2, n3, rtab64.t[ksel]);
-                        st_fe(T + j, lo);
-                        st_fe(T + j + q, hi);
-                    } else {
-                        lo = fe_fold_fixed<F>(n0, n2, rtab);  // the challenge enters as precomputed multiples (fe_mul_fixed)
-                        st_fe(T + j, lo);
-                        hi = fe_fold_fixed<F>(n1, n3, rtab);
-                        st_fe(T + j + q, hi);
-                    }
-                    if (nj < q) {
-                        n0 = ld_fe_stream(NT + nj); n2 = ld_fe_stream(NT + nj + 2 * q);
-                        n1 = ld_fe_stream(NT + nj + q); n3 = ld_fe_stream(NT + nj + 3 * q);
-                    }
-                } else {
-                    Fe x0 = ld_fe_stream(T + j), x2 = ld_fe_stream(T + j + 2 * q);
-                    Fe x1 = ld_fe_stream(T + j + q), x3 = ld_fe_stream(T + j + 3 * q);
-                    if (F64) {
-                        fe_fold_fixed_f64_x2<F>(lo, hi, x0, x1, x2, x3, rtab64.t[ksel]);
-                        st_fe(T + j, lo);
-                        st_fe(T + j + q, hi);
-                    } else {
-                        lo = fe_fold_fixed<F>(x0, x2, rtab);
-                        st_fe(T + j, lo);
-                        hi = fe_fold_fixed<F>(x1, x3, rtab);
-                        st_fe(T + j + q, hi);
-                    }
-                }
-            } else {  // T has 2q entries: the pair is (j, j+q)
-                lo = n0;
-                hi = n1;
-                if (nj < q) {
-                    n0 = ld_fe_stream(NT + nj);
-                    n1 = ld_fe_stream(NT + nj + q);
-                }
-            }
-            const bool last = (k == m - 1);
-            if (TOOM) {  // pr[0..3] live at t = 0, 1, -1, inf ; m == 3
-                const Fe d = fe_sub<F>(hi, lo);
-                if (k == 0) {
-                    pr[0] = lo; pr[1] = hi; pr[3] = d; pr[2] = fe_sub<F>(lo, d);
-                } else if (!last) {
-                    pr[0] = fe_mul<F>(lo, pr[0]);
-                    pr[1] = fe_mul<F>(hi, pr[1]);
-                    pr[3] = fe_mul<F>(d, pr[3]);
-                    const Fe s02 = fe_add<F>(pr[0], pr[3]);
-                    pr[2] = fe_sub<F>(fe_add<F>(s02, s02), pr[1]);
-                } else {
-                    uint32_t w[16];
-                    fe_mul_wide(w, lo, pr[0]); accw_add16(accw, w);
-                    fe_mul_wide(w, hi, pr[1]); accw_add16(accw + 5 * kThreads, w);
-                    fe_mul_wide(w, fe_sub<F>(lo, d), pr[2]); accw_add16(accw + 2 * 5 * kThreads, w);
-                    fe_mul_wide(w, d, pr[3]); accw_add16(accw + 3 * 5 * kThreads, w);
-                }
-            } else if (k == 0) {
-                pr[0] = lo;
-                if (D >= 1) pr[1] = hi;
-                if (D >= 2) {
-                    Fe d = fe_sub<F>(hi, lo);
-#pragma unroll
-                    for (int t = 2; t <= D; t++) {
-                        hi = fe_add<F>(hi, d);
-                        pr[t] = hi;
-                    }
-                }
-                if (last) {  // m == 1: the terms are the table values themselves
-#pragma unroll
-                    for (int t = 0; t <= D; t++) accw_add_hi(accw + t * 5 * kThreads, pr[t]);
-                }
+            const uint64_t njw = more_k ? jw : (uint64_t)wc.cn * 32;
+            const bool nok = more_k || WarpChunks<!TOOM>::live(wc.cn, q);
+            if (FOLD) {
+                const Fe x0 = lds_fe(slab + lane), x1 = lds_fe(slab + 32 + lane);
+                const Fe x2 = lds_fe(slab + 64 + lane), x3 = lds_fe(slab + 96 + lane);
+                __syncwarp();  // every lane has its elements: the slab may be overwritten
+                if (nok && lane == 0) issue(njw, more_k ? k + 1 : 0);
+                fold_pair<F, F64>(lo, hi, x0, x1, x2, x3, rtab, rtab64.t[ksel]);
+                st_fe(T + j, lo);
+                st_fe(T + j + q, hi);
             } else {
-                uint32_t w[16];
-                if (last) { fe_mul_wide(w, lo, pr[0]); accw_add16(accw, w); } else pr[0] = fe_mul<F>(lo, pr[0]);
-                if (D >= 2) lo = fe_sub<F>(hi, lo);  // lo := d
-                if (D >= 1) {
-                    if (last) { fe_mul_wide(w, hi, pr[1]); accw_add16(accw + 5 * kThreads, w); } else pr[1] = fe_mul<F>(hi, pr[1]);
-                }
-#pragma unroll
-                for (int t = 2; t <= D; t++) {
-                    hi = fe_add<F>(hi, lo);
-                    if (last) { fe_mul_wide(w, hi, pr[t]); accw_add16(accw + t * 5 * kThreads, w); } else pr[t] = fe_mul<F>(hi, pr[t]);
-                }
+                lo = lds_fe(slab + lane);
+                hi = lds_fe(slab + 32 + lane);
+                __syncwarp();
+                if (nok && lane == 0) issue(njw, more_k ? k + 1 : 0);
             }
+            item_terms<F, D, TOOM>(k, k == m - 1, lo, hi, pr, accw);
         }
+        wc.advance(ra);
     }
     Fe acc[D + 1];
 #pragma unroll 1
-    for (int t = 0; t <= D; t++) acc[t] = accw_reduce<F>(accw + t * 5 * kThreads);
+    for (int t = 0; t <= D; t++) acc[t] = accw_reduce<F>(accw_at(accw, t));
     __syncthreads();
     reduce_publish<F, D + 1, TOOM>(acc, ra);
 }
@@ -428,8 +626,28 @@ inline unsigned grid_for(uint64_t items, int threads, int num_sms, int bpsm) {
     if (need < 1) need = 1;
     return (unsigned)(need < cap ? need : cap);
 }
+// ZK_B200_SCHED=static keeps the grid-stride split (A/B measurements); default: dynamic chunks.
+inline bool dynamic_chunks() {
+    static const bool on = [] {
+        const char* e = std::getenv("ZK_B200_SCHED");
+        return !(e && e[0] == 's');
+    }();
+    return on;
+}
+// Chunks per request of the work counter.  One same-address atomic per 32 items is fine when an item costs three
+// factors of multiplications; with one or two factors the counter itself becomes the bottleneck (measured: about
+// 0.8e9 same-address atomics per second), so lighter items are handed out in groups.  ZK_B200_GROUP_LOG2 overrides.
+inline int chunk_group_log2(int m) {
+    static const int forced = [] {
+        const char* e = std::getenv("ZK_B200_GROUP_LOG2");
+        return e ? std::atoi(e) : -1;
+    }();
+    if (forced >= 0) return forced > 8 ? 8 : forced;
+    return m >= 3 ? 0 : (m == 2 ? 2 : 4);  // the Toom kernels (m == 3, D == 3) are compiled without grouping
+}
 inline ReduceArgs make_ra(const ReduceScratch& s, int slot) {
-    return ReduceArgs{s.block_partials, s.ticket, s.result_dev, s.result_host_devptr, slot, s.flag_host_devptr, s.seq, s.lanes};
+    return ReduceArgs{s.block_partials, s.ticket, s.result_dev, s.result_host_devptr, slot, s.flag_host_devptr, s.seq, s.lanes,
+                      dynamic_chunks() ? 1 : 0, 0};
 }
 template <class F>
 Fe small_constant(unsigned t);  // Montgomery form of small integer t (host side)
@@ -465,9 +683,34 @@ inline bool fold_on_f64() {
     return on;
 }
 
+// ZK_B200_STAGE=reg selects the register-prefetch kernel for A/B measurements; default: TMA staging.
+inline bool stage_with_tma() {
+    static const bool on = [] {
+        const char* e = std::getenv("ZK_B200_STAGE");
+        return !(e && e[0] == 'r');
+    }();
+    return on;
+}
+
 template <class F, int D, bool FOLD, bool TOOM, bool F64>
 cudaError_t do_round_v(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st) {
-    constexpr size_t smem = (size_t)(D + 1) * 5 * kThreads * sizeof(uint4);
+    const FixedMul tab = (FOLD && !F64) ? make_fixed<F>(r) : FixedMul{};
+    const FixedMulF64Sel tab64 = F64 ? make_fixed_f64<F>(r) : FixedMulF64Sel{};
+    ReduceArgs ra = make_ra(s, 0);
+    ra.group_log2 = chunk_group_log2(m);
+    if (q % 32 == 0 && stage_with_tma()) {
+        constexpr size_t smem = accw_bytes(D + 1) + stage_bytes<FOLD>();
+        static int bpsm = [] {
+            cudaFuncSetAttribute(round_kernel_tma<F, D, FOLD, TOOM, F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel_tma<F, D, FOLD, TOOM, F64>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
+            return nb;
+        }();
+        unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
+        round_kernel_tma<F, D, FOLD, TOOM, F64><<<grid, kThreads, smem, st>>>(tabs, m, q, tab, tab64, ra);
+        return cudaGetLastError();
+    }
+    constexpr size_t smem = accw_bytes(D + 1);
     static int bpsm = [] {
         cudaFuncSetAttribute(round_kernel<F, D, FOLD, TOOM, F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int nb = 0;
@@ -475,8 +718,7 @@ cudaError_t do_round_v(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, co
         return nb;
     }();
     unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
-    round_kernel<F, D, FOLD, TOOM, F64><<<grid, kThreads, smem, st>>>(
-        tabs, m, q, (FOLD && !F64) ? make_fixed<F>(r) : FixedMul{}, F64 ? make_fixed_f64<F>(r) : FixedMulF64Sel{}, make_ra(s, 0));
+    round_kernel<F, D, FOLD, TOOM, F64><<<grid, kThreads, smem, st>>>(tabs, m, q, tab, tab64, ra);
     return cudaGetLastError();
 }
 template <class F, int D, bool FOLD, bool TOOM = false>
