@@ -324,18 +324,25 @@ def run_ours(args):
     fused_s = (sum(fused_ms) / len(fused_ms)) * 1e-3
     achieved = fused_bytes / fused_s / 1e9
     fused_muls = (2 * m + (d + 1) * (m - 1)) * (local_n0 // 4)
-    # IMAD.WIDE.U32 actually issued per item of the fused step (field.cuh): a fold is a fixed-multiplier product
-    # (76), an intermediate product 112, the last product of a term 64 (unreduced); the cubic/3-factor case
-    # carries its terms at the Toom points (3 intermediate products instead of 4)
+    # Instructions actually issued per item of the fused step.  Product multiplications (field.cuh): an intermediate
+    # product is 112 IMAD.WIDE.U32, the last product of a term 64 (unreduced); the cubic/3-factor case carries its
+    # terms at the Toom points (3 intermediate products instead of 4).  Folds: with two or more factors they run on
+    # the FP64 pipe (field_f64.cuh: 128 DFMA + 6 IMAD.WIDE each), a single table folds on the integer pipe (76).
     if m == 1:
         prod_wide = 0
     elif m == 3 and d == 3:
         prod_wide = 3 * 112 + 4 * 64
     else:
         prod_wide = (m - 2) * (d + 1) * 112 + (d + 1) * 64
-    wide_per_item = 2 * m * 76 + prod_wide
-    wide_per_s = wide_per_item * (local_n0 // 4) / fused_s
-    mb = ctx.microbench(FIELD) if not args.no_microbench else {"fe_mul_per_s": float("nan"), "imad_wide_per_s": float("nan")}
+    fold_pipe = os.environ.get("ZK_B200_FOLD_PIPE", "f64" if m >= 2 else "int")[0]
+    fold_wide, fold_dfma = (6, 128) if fold_pipe == "f" else (76, 0)
+    wide_per_item = 2 * m * fold_wide + prod_wide
+    dfma_per_item = 2 * m * fold_dfma
+    items = local_n0 // 4
+    wide_per_s = wide_per_item * items / fused_s
+    dfma_per_s = dfma_per_item * items / fused_s
+    nan = float("nan")
+    mb = ctx.microbench(FIELD) if not args.no_microbench else {"fe_mul_per_s": nan, "imad_wide_per_s": nan, "dfma_per_s": nan, "fe_mul_fixed_per_s": nan}
     traffic, traffic_src = ncu_traffic(n, m, d, world)
     roofline = {"bound": "hbm", "kernel": f"round_kernel<Fr381,{d},FOLD=true> (first fused fold+round-sum step, m={m})", "achieved": achieved,
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_src,
@@ -345,6 +352,12 @@ def run_ours(args):
                              "frac": wide_per_s / mb["imad_wide_per_s"], "field_mul_per_s": fused_muls / fused_s,
                              "frac_textbook_128_per_mul": fused_muls / fused_s * 128 / mb["imad_wide_per_s"],
                              "standalone_fe_mul_per_s": mb["fe_mul_per_s"]},
+                "fp64_pipe": {"bound": "DFMA issue rate (the folds: exact FP64 dot products against multiples of the challenge)",
+                              "dfma_per_item": dfma_per_item, "achieved_dfma_per_s": dfma_per_s, "peak_dfma_per_s": mb["dfma_per_s"],
+                              "frac": dfma_per_s / mb["dfma_per_s"], "standalone_fe_mul_fixed_per_s": mb["fe_mul_fixed_per_s"]},
+                # both pipes run concurrently: the time the two instruction streams would need at their measured peak
+                # issue rates, whichever is longer, over the measured launch time
+                "pipe_frac": max(wide_per_s / mb["imad_wide_per_s"], dfma_per_s / mb["dfma_per_s"]),
                 "whole_prove": {"alg_bytes": alg_bytes(n, m) / world, "gbs": alg_bytes(n, m) / world / (ms_per_step * 1e-3) / 1e9}}
 
     # ---- CPU baseline beside it (bounded sample, rank 0, N = 1 only) ----------------------------------------------
@@ -359,7 +372,7 @@ def run_ours(args):
     line = {
         "metric": "sumcheck_prove_field_mul_per_s", "value": value, "unit": "field-mul/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs, IMAD.WIDE)", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs; IMAD.WIDE products, exact FP64 folds)", "data": "synthetic",
         "config": workload_config(n, m, d, world), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "cpu_baseline": cpu, "prove_ms": ms_per_step, "proof_keccak": proof_digest, "verified": verified,
         "round_kernel_ms": [round(x, 4) for x in ctx.last_round_ms()], "step_ms": [round(x, 3) for x in step_ms], "microbench": mb,

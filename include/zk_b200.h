@@ -212,6 +212,8 @@ typedef struct zk_microbench {
     double copy_gbs;     /* 256-bit streaming copy, read+write GB/s */
     double read_gbs;
     double sm_clock_mhz;
+    double dfma_per_s;       /* FP64 FMA issued per second, whole chip (the folds run on this pipe) */
+    double fe_mul_fixed_per_s; /* stand-alone fixed-multiplier products per second, FP64-pipe version */
 } zk_microbench;
 ZK_API int zk_microbench_run(zk_ctx* ctx, int field, zk_microbench* out);
 

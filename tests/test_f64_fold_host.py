@@ -1,0 +1,20 @@
+"""CPU suite: the FP64 fixed-multiplier product of the fold (zk_b200/csrc/field_f64.cuh) replayed on the host.
+
+The device folds l + r (h - l) with exact double-precision dot products (every intermediate an integer < 2^53), so the
+same header compiles for the host and its arithmetic can be checked bit for bit without a GPU against the word-serial
+Montgomery multiplier of host_field.hpp: the reference's `left - a * (left - right)`
+(polynomial/src/multilinear/evaluation_form.rs:68) for random and extreme operands, both fields."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_f64_fold_matches_host_multiplier(tmp_path):
+    exe = str(tmp_path / "test_f64_fold")
+    cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "zk_b200", "csrc"),
+           os.path.join(ROOT, "tests", "cpp", "test_f64_fold.cpp"), "-o", exe]
+    subprocess.run(cmd, check=True, capture_output=True, timeout=300)
+    out = subprocess.run([exe], check=True, capture_output=True, timeout=300, text=True).stdout
+    assert "0 mismatches" in out, out
+    assert "4800000 checked" in out, out

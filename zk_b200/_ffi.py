@@ -25,7 +25,7 @@ STATUS_NAMES = {
 
 class zk_microbench(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("imad_wide_per_s", "imad_lo_per_s", "iadd3_per_s", "mixed_per_s", "fe_mul_per_s",
-                                          "copy_gbs", "read_gbs", "sm_clock_mhz")]
+                                          "copy_gbs", "read_gbs", "sm_clock_mhz", "dfma_per_s", "fe_mul_fixed_per_s")]
 
 
 # name -> (restype, argtypes): every symbol include/zk_b200.h declares

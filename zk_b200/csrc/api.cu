@@ -1187,6 +1187,8 @@ int zk_microbench_run(zk_ctx* ctx, int field, zk_microbench* out) {
     out->copy_gbs = r.copy_gbs;
     out->read_gbs = r.read_gbs;
     out->sm_clock_mhz = r.sm_clock_mhz;
+    out->dfma_per_s = r.dfma_per_s;
+    out->fe_mul_fixed_per_s = r.fe_mul_fixed_per_s;
     return ZK_OK;
 }
 

@@ -31,6 +31,13 @@ struct alignas(16) FixedMulF64 {
     double t[16][8];  // t[i][j] = limb j of r * 2^(16 i + 32) mod p
 };
 
+// Two identical copies, indexed in kernels by a value that is always 0 but loop-variant in ptxas's eyes: with a
+// loop-invariant address ptxas hoists all 128 table entries out of the loop, runs out of uniform registers and
+// spills them to local memory (see `ksel` in round_kernel).
+struct FixedMulF64Sel {
+    FixedMulF64 t[2];
+};
+
 namespace detail {
 #ifdef __CUDA_ARCH__
 __device__ __forceinline__ double f64_from_bits(uint32_t hi, uint32_t lo) { return __hiloint2double((int)hi, (int)lo); }

@@ -96,6 +96,8 @@ struct MicrobenchResult {
     double copy_gbs;            // 256-bit streaming copy GB/s (read+write)
     double read_gbs;            // 256-bit streaming read GB/s
     double sm_clock_mhz;        // clock64-derived SM clock during the IMAD run
+    double dfma_per_s;          // independent DFMA per second, whole chip
+    double fe_mul_fixed_per_s;  // standalone fe_mul_fixed_f64 (FP64-pipe fixed-multiplier product) per second
 };
 cudaError_t run_microbench(int field, MicrobenchResult* out, cudaStream_t stream);
 

@@ -39,10 +39,6 @@ constexpr int kThreads = 128;
 
 constexpr int kWarps = kThreads / 32;
 
-struct FixedMulF64Sel {
-    FixedMulF64 t[2];  // two identical copies, see `ksel` in round_kernel
-};
-
 __device__ __forceinline__ Fe ld_fe_cg(const Fe* p) {  // L2-coherent load (other blocks' partials)
     Fe r;
     asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -75,8 +71,6 @@ struct ReduceArgs {
     unsigned* flag_host;  // mapped pinned word the host spins on (saves a stream synchronisation per round)
     unsigned seq;
     uint64_t* lanes;      // sharded runs: one 32-bit limb per u64 lane, the input of the exact ncclSum all-reduce
-    int dynamic;          // round kernels: chunks from the global work counter (WarpChunks) instead of a static split
-    int group_log2;       // round kernels: a warp takes 2^group_log2 consecutive chunks per request
 };
 constexpr int kWorkCounterOffset = 32;  // the work counter lives 128 bytes after the ticket (own cache line)
 
@@ -321,52 +315,39 @@ __device__ __forceinline__ void fold_pair(Fe& lo, Fe& hi, const Fe& x0, const Fe
 // SM): the schedulers favour some warps, those finish their share early and the rest run out the kernel at low
 // occupancy.  So each warp takes its first two chunks statically and every later one from a global counter
 // (one atomicAdd per 32 items, requested a whole chunk ahead so its latency is hidden); the last block resets
-// the counter together with the ticket.  ra.dynamic == 0 keeps the static split (A/B measurements).
-template <bool GROUPED>  // GROUPED = false: one chunk per request (three-factor items), two registers less
-struct WarpChunks {      // 32-bit chunk ids: tables of up to 2^37 items
-    uint32_t c, cn;           // current chunk, next chunk
-    uint32_t gn;              // GROUPED: the group after the one `c` is in
-    uint32_t fetched;
-    __device__ __forceinline__ WarpChunks(const ReduceArgs& ra, int warp) {
-        const uint32_t tw = gridDim.x * kWarps, wid = blockIdx.x * kWarps + warp;
-        if (GROUPED) {
-            c = wid << ra.group_log2;
-            gn = wid + tw;
-            cn = ra.group_log2 ? c + 1 : gn;
-        } else {
-            c = wid;
-            cn = wid + tw;
-        }
+// the counter together with the ticket.  DYN = false keeps the static split: single-table sums are HBM bound and
+// so light per chunk that the counter itself (about 0.8e9 same-address atomics per second, measured) would bind.
+template <bool DYN>
+struct WarpChunks {  // 32-bit chunk ids: tables of up to 2^37 items
+    uint32_t c;        // current chunk
+    uint32_t cn_dyn;   // DYN: next chunk (static: c + number of warps, not stored)
+    uint32_t fetched;  // DYN
+    __device__ __forceinline__ WarpChunks(int warp) {
+        c = blockIdx.x * kWarps + warp;
+        if (DYN) cn_dyn = c + gridDim.x * kWarps;
         fetched = 0;
     }
+    __device__ __forceinline__ uint32_t cn() const { return DYN ? cn_dyn : c + gridDim.x * kWarps; }
     __device__ __forceinline__ static bool live(uint32_t chunk, uint64_t q) { return (uint64_t)chunk * 32 < q; }
-    // top of a chunk: at the first chunk of a group ask for the group after next
-    __device__ __forceinline__ void request(const ReduceArgs& ra, int lane) {
-        const uint32_t gmask = GROUPED ? (1u << ra.group_log2) - 1u : 0u;
-        if (ra.dynamic && lane == 0 && (c & gmask) == 0) fetched = atomicAdd(ra.ticket + kWorkCounterOffset, 1u);
+    __device__ __forceinline__ void request(const ReduceArgs& ra, int lane) {  // top of a chunk: ask for the chunk after next
+        if (DYN && lane == 0) fetched = atomicAdd(ra.ticket + kWorkCounterOffset, 1u);
     }
-    // bottom of a chunk (all lanes converged)
-    __device__ __forceinline__ void advance(const ReduceArgs& ra) {
-        const uint32_t tw = gridDim.x * kWarps;
-        if (GROUPED) {
-            const uint32_t gmask = (1u << ra.group_log2) - 1u;
-            if (((c + 1) & gmask) == 0)  // `c` was the last chunk of its group (warp-uniform)
-                gn = ra.dynamic ? __shfl_sync(0xffffffffu, fetched, 0) + 2 * tw : gn + tw;
-            c = cn;
-            cn = ((c + 1) & gmask) ? c + 1 : gn << ra.group_log2;
+    __device__ __forceinline__ void advance() {  // bottom of a chunk (all lanes converged)
+        if (DYN) {
+            const uint32_t cnn = __shfl_sync(0xffffffffu, fetched, 0) + 2 * gridDim.x * kWarps;
+            c = cn_dyn;
+            cn_dyn = cnn;
         } else {
-            const uint32_t cnn = ra.dynamic ? __shfl_sync(0xffffffffu, fetched, 0) + 2 * tw : cn + tw;
-            c = cn;
-            cn = cnn;
+            c += gridDim.x * kWarps;
         }
     }
 };
 
-// ---- register-prefetch variant (any q; the only variant for q < 32) -----------------------------------------
+// ---- the round kernel -----------------------------------------------------------------------------------------
 // F64 (only with FOLD): the folds run on the FP64 pipe (field_f64.cuh: exact DFMA dot products against 16 host-made
 // multiples of the challenge, one Montgomery row) instead of fe_mul_fixed's 76 wide multiplies.
-template <class F, int D, bool FOLD, bool TOOM = false, bool F64 = false>
-__global__ void __launch_bounds__(kThreads, (D <= 1) ? ZK_RK_MINBLOCKS_D1 : (D == 2 ? ZK_RK_MINBLOCKS_D2 : ZK_RK_MINBLOCKS_D3))
+template <class F, int D, bool FOLD, bool TOOM = false, bool F64 = false, bool DYN = false>
+__global__ void __launch_bounds__(kThreads, (D <= 1) ? (FOLD ? ZK_RK_MINBLOCKS_D1 : ZK_RK_MINBLOCKS_D1 - 1) : (D == 2 ? ZK_RK_MINBLOCKS_D2 : ZK_RK_MINBLOCKS_D3))
     round_kernel(TablePtrs tabs, int m, uint64_t q, const __grid_constant__ FixedMul rtab,
                  const __grid_constant__ FixedMulF64Sel rtab64, ReduceArgs ra) {
     static_assert(!TOOM || D == 3, "the Toom point set is wired for cubics");
@@ -378,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? ZK_RK_MINBLOCKS_D1 : (D =
     __syncthreads();
     const Accw accw = accw_base(accw_all, D + 1);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpChunks<!TOOM> wc(ra, warp);
+    WarpChunks<DYN> wc(warp);
     // Software pipelining of the global loads.  Round 0 (no fold) keeps the pair of the next (item, factor) in
     // flight while this one is multiplied.  The fused kernel issues the four loads of the next (item, factor)
     // right AFTER this factor's folds (when x0..x3 are dead) so they land during the product multiplications
@@ -398,9 +379,9 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? ZK_RK_MINBLOCKS_D1 : (D =
         }
     }
 #pragma unroll 1
-    while (WarpChunks<!TOOM>::live(wc.c, q)) {
+    while (WarpChunks<DYN>::live(wc.c, q)) {
         wc.request(ra, lane);
-        const uint64_t j = (uint64_t)wc.c * 32 + lane, jn = (uint64_t)wc.cn * 32 + lane;
+        const uint64_t j = (uint64_t)wc.c * 32 + lane, jn = (uint64_t)wc.cn() * 32 + lane;
         const bool nvalid = jn < q;
         if (j < q) {  // false only in the single ragged chunk of a table with fewer than 32 items
             Fe pr[D + 1];
@@ -442,122 +423,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? ZK_RK_MINBLOCKS_D1 : (D =
                 item_terms<F, D, TOOM>(k, k == m - 1, lo, hi, pr, accw);
             }
         }
-        wc.advance(ra);
-    }
-    Fe acc[D + 1];
-#pragma unroll 1
-    for (int t = 0; t <= D; t++) acc[t] = accw_reduce<F>(accw_at(accw, t));
-    __syncthreads();
-    reduce_publish<F, D + 1, TOOM>(acc, ra);
-}
-
-// ---- TMA-staged variant (q a multiple of 32) ---------------------------------------------------------------
-// The register-prefetch kernel above keeps the next factor's four elements in 32 registers across the product
-// multiplications; at the 128-register cap ptxas spills part of them right after the load, and that spill store
-// waits out the full HBM latency (ncu: 7-14 % of all stall samples on one STL).  Here each warp owns a 4 KB slab
-// of shared memory and one mbarrier: lane 0 issues cp.async.bulk (TMA) copies of the warp's NS contiguous 1 KB
-// runs — T[jw .. jw+32) at offsets 0, q, 2q, 3q — for the NEXT (item, factor) as soon as the current one has been
-// read out of the slab, so a whole factor step (~4 us) hides the latency, no register is tied up by data in flight
-// and nothing is spilled.  Warp-private: no block-level barrier in the loop.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "MBAR_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra MBAR_DONE;\n\t"
-        "bra MBAR_WAIT;\n\t"
-        "MBAR_DONE:\n\t"
-        "}" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ Fe lds_fe(const Fe* p) {
-    Fe r;
-    const uint32_t a = smem_u32(p);
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]) : "r"(a));
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "r"(a));
-    return r;
-}
-
-template <bool FOLD>
-__host__ __device__ constexpr size_t stage_bytes() { return (size_t)kWarps * (FOLD ? 4 : 2) * 32 * sizeof(Fe); }
-
-template <class F, int D, bool FOLD, bool TOOM = false, bool F64 = false>
-__global__ void __launch_bounds__(kThreads, (D <= 1) ? ZK_RK_MINBLOCKS_D1 : (D == 2 ? ZK_RK_MINBLOCKS_D2 : ZK_RK_MINBLOCKS_D3))
-    round_kernel_tma(TablePtrs tabs, int m, uint64_t q, const __grid_constant__ FixedMul rtab,
-                     const __grid_constant__ FixedMulF64Sel rtab64, ReduceArgs ra) {
-    static_assert(!TOOM || D == 3, "the Toom point set is wired for cubics");
-    static_assert(!F64 || FOLD, "the FP64 variant only changes the folds");
-    constexpr int NS = FOLD ? 4 : 2;  // contiguous runs per (warp, factor): offsets 0, q, (2q, 3q)
-    extern __shared__ uint4 smem_all[];  // accw_bytes(D+1) | stage_bytes<FOLD>()
-    __shared__ Fe* s_tab[kMaxFactors];
-    __shared__ __align__(8) unsigned long long s_bar[kWarps];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < kMaxFactors) s_tab[threadIdx.x] = tabs.t[threadIdx.x];
-    accw_zero(smem_all, D + 1);
-    const uint32_t bar = smem_u32(&s_bar[warp]);
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const Accw accw = accw_base(smem_all, D + 1);
-    Fe* slab = reinterpret_cast<Fe*>(reinterpret_cast<unsigned char*>(smem_all) + accw_bytes(D + 1)) + warp * NS * 32;
-    const uint32_t slab_u32 = smem_u32(slab);
-    WarpChunks<!TOOM> wc(ra, warp);  // q % 32 == 0: every chunk is a full 1 KB run in each stream
-    auto issue = [&](uint64_t jw, int k) {  // lane 0 only
-        const Fe* T = s_tab[k] + jw;
-        mbar_expect_tx(bar, NS * 32 * (uint32_t)sizeof(Fe));
-#pragma unroll
-        for (int s = 0; s < NS; s++) tma_load_1d(slab_u32 + s * 32 * (uint32_t)sizeof(Fe), T + s * q, 32 * (uint32_t)sizeof(Fe), bar);
-    };
-    if (WarpChunks<!TOOM>::live(wc.c, q) && lane == 0) issue((uint64_t)wc.c * 32, 0);
-    uint32_t parity = 0;
-#pragma unroll 1
-    while (WarpChunks<!TOOM>::live(wc.c, q)) {
-        wc.request(ra, lane);
-        const uint64_t jw = (uint64_t)wc.c * 32, j = jw + lane;
-        Fe pr[D + 1];
-#pragma unroll 1
-        for (int k = 0; k < m; k++) {
-            Fe* T = s_tab[k];
-            const int ksel = F64 ? (k >> 16) : 0;  // always 0, see round_kernel
-            mbar_wait(bar, parity);
-            parity ^= 1;
-            Fe lo, hi;
-            const bool more_k = (k + 1 < m);
-            const uint64_t njw = more_k ? jw : (uint64_t)wc.cn * 32;
-            const bool nok = more_k || WarpChunks<!TOOM>::live(wc.cn, q);
-            if (FOLD) {
-                const Fe x0 = lds_fe(slab + lane), x1 = lds_fe(slab + 32 + lane);
-                const Fe x2 = lds_fe(slab + 64 + lane), x3 = lds_fe(slab + 96 + lane);
-                __syncwarp();  // every lane has its elements: the slab may be overwritten
-                if (nok && lane == 0) issue(njw, more_k ? k + 1 : 0);
-                fold_pair<F, F64>(lo, hi, x0, x1, x2, x3, rtab, rtab64.t[ksel]);
-                st_fe(T + j, lo);
-                st_fe(T + j + q, hi);
-            } else {
-                lo = lds_fe(slab + lane);
-                hi = lds_fe(slab + 32 + lane);
-                __syncwarp();
-                if (nok && lane == 0) issue(njw, more_k ? k + 1 : 0);
-            }
-            item_terms<F, D, TOOM>(k, k == m - 1, lo, hi, pr, accw);
-        }
-        wc.advance(ra);
+        wc.advance();
     }
     Fe acc[D + 1];
 #pragma unroll 1
@@ -634,20 +500,8 @@ inline bool dynamic_chunks() {
     }();
     return on;
 }
-// Chunks per request of the work counter.  One same-address atomic per 32 items is fine when an item costs three
-// factors of multiplications; with one or two factors the counter itself becomes the bottleneck (measured: about
-// 0.8e9 same-address atomics per second), so lighter items are handed out in groups.  ZK_B200_GROUP_LOG2 overrides.
-inline int chunk_group_log2(int m) {
-    static const int forced = [] {
-        const char* e = std::getenv("ZK_B200_GROUP_LOG2");
-        return e ? std::atoi(e) : -1;
-    }();
-    if (forced >= 0) return forced > 8 ? 8 : forced;
-    return m >= 3 ? 0 : (m == 2 ? 2 : 4);  // the Toom kernels (m == 3, D == 3) are compiled without grouping
-}
 inline ReduceArgs make_ra(const ReduceScratch& s, int slot) {
-    return ReduceArgs{s.block_partials, s.ticket, s.result_dev, s.result_host_devptr, slot, s.flag_host_devptr, s.seq, s.lanes,
-                      dynamic_chunks() ? 1 : 0, 0};
+    return ReduceArgs{s.block_partials, s.ticket, s.result_dev, s.result_host_devptr, slot, s.flag_host_devptr, s.seq, s.lanes};
 }
 template <class F>
 Fe small_constant(unsigned t);  // Montgomery form of small integer t (host side)
@@ -674,57 +528,38 @@ FixedMulF64Sel make_fixed_f64(const Fe& r) {
     return t;
 }
 
-// ZK_B200_FOLD_PIPE=f64 selects the FP64-pipe folds (field_f64.cuh) for A/B measurements; default: integer pipe.
-inline bool fold_on_f64() {
-    static const bool on = [] {
+// Which pipe folds: FP64 (field_f64.cuh) for items of two or more factors, where the product multiplications keep
+// the integer-multiply pipe busy (measured -3 % on the fused degree-3 step, -1.5 % at degree 2); the integer pipe
+// for a single table (HBM bound: the longer FP64 instruction stream only costs).  ZK_B200_FOLD_PIPE=int|f64 forces one.
+inline bool fold_on_f64(int m) {
+    static const int forced = [] {
         const char* e = std::getenv("ZK_B200_FOLD_PIPE");
-        return e && e[0] == 'f';
+        return !e ? -1 : (e[0] == 'f' ? 1 : 0);
     }();
-    return on;
+    return forced >= 0 ? forced == 1 : m >= 2;
 }
 
-// ZK_B200_STAGE=reg selects the register-prefetch kernel for A/B measurements; default: TMA staging.
-inline bool stage_with_tma() {
-    static const bool on = [] {
-        const char* e = std::getenv("ZK_B200_STAGE");
-        return !(e && e[0] == 'r');
-    }();
-    return on;
-}
-
-template <class F, int D, bool FOLD, bool TOOM, bool F64>
+template <class F, int D, bool FOLD, bool TOOM, bool F64, bool DYN>
 cudaError_t do_round_v(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st) {
     const FixedMul tab = (FOLD && !F64) ? make_fixed<F>(r) : FixedMul{};
     const FixedMulF64Sel tab64 = F64 ? make_fixed_f64<F>(r) : FixedMulF64Sel{};
-    ReduceArgs ra = make_ra(s, 0);
-    ra.group_log2 = chunk_group_log2(m);
-    if (q % 32 == 0 && stage_with_tma()) {
-        constexpr size_t smem = accw_bytes(D + 1) + stage_bytes<FOLD>();
-        static int bpsm = [] {
-            cudaFuncSetAttribute(round_kernel_tma<F, D, FOLD, TOOM, F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            int nb = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel_tma<F, D, FOLD, TOOM, F64>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
-            return nb;
-        }();
-        unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
-        round_kernel_tma<F, D, FOLD, TOOM, F64><<<grid, kThreads, smem, st>>>(tabs, m, q, tab, tab64, ra);
-        return cudaGetLastError();
-    }
     constexpr size_t smem = accw_bytes(D + 1);
     static int bpsm = [] {
-        cudaFuncSetAttribute(round_kernel<F, D, FOLD, TOOM, F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(round_kernel<F, D, FOLD, TOOM, F64, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<F, D, FOLD, TOOM, F64>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<F, D, FOLD, TOOM, F64, DYN>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
         return nb;
     }();
     unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
-    round_kernel<F, D, FOLD, TOOM, F64><<<grid, kThreads, smem, st>>>(tabs, m, q, tab, tab64, ra);
+    round_kernel<F, D, FOLD, TOOM, F64, DYN><<<grid, kThreads, smem, st>>>(tabs, m, q, tab, tab64, make_ra(s, 0));
     return cudaGetLastError();
 }
 template <class F, int D, bool FOLD, bool TOOM = false>
 cudaError_t do_round(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st) {
-    if (FOLD && fold_on_f64()) return do_round_v<F, D, FOLD, TOOM, FOLD>(tabs, m, q, r, s, st);
-    return do_round_v<F, D, FOLD, TOOM, false>(tabs, m, q, r, s, st);
+    const bool dyn = m >= 2 && dynamic_chunks();
+    if (FOLD && fold_on_f64(m))
+        return dyn ? do_round_v<F, D, FOLD, TOOM, FOLD, true>(tabs, m, q, r, s, st) : do_round_v<F, D, FOLD, TOOM, FOLD, false>(tabs, m, q, r, s, st);
+    return dyn ? do_round_v<F, D, FOLD, TOOM, false, true>(tabs, m, q, r, s, st) : do_round_v<F, D, FOLD, TOOM, false, false>(tabs, m, q, r, s, st);
 }
 template <class F, bool FOLD>
 cudaError_t do_round_deg(const TablePtrs& tabs, int m, int degree, uint64_t q, const Fe& r, const ReduceScratch& s,

@@ -3,6 +3,8 @@
 // field-mul ceiling of this multiplier) and 256-bit streaming bandwidth.  SURVEY.md 8d asks for the
 // integer peak to be measured rather than assumed; MEASURED_PEAKS.json only carries HBM and bf16.
 #include "kernels.h"
+#include "field_f64.cuh"
+#include "host_field.hpp"
 
 namespace zk {
 namespace {
@@ -89,7 +91,38 @@ __global__ void __launch_bounds__(kThreads) mixed_kernel(uint32_t seed, uint64_t
     uint64_t s = a0 ^ a1 ^ a2 ^ a3 ^ b0 ^ b1 ^ b2 ^ b3;
     if (s == 0x1234567) sink[0] = s;
 }
+__global__ void __launch_bounds__(kThreads) dfma_kernel(uint32_t seed, double* sink) {
+    double a0 = 1.0 + seed * 1e-9 + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double x = 1.0000001 + seed * 1e-12, y = 1e-13 * threadIdx.x;
+#pragma unroll 1
+    for (int i = 0; i < kIters; i++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            asm volatile(
+                "fma.rn.f64 %0, %0, %8, %9;\n\tfma.rn.f64 %1, %1, %8, %9;\n\tfma.rn.f64 %2, %2, %8, %9;\n\t"
+                "fma.rn.f64 %3, %3, %8, %9;\n\tfma.rn.f64 %4, %4, %8, %9;\n\tfma.rn.f64 %5, %5, %8, %9;\n\t"
+                "fma.rn.f64 %6, %6, %8, %9;\n\tfma.rn.f64 %7, %7, %8, %9;"
+                : "+d"(a0), "+d"(a1), "+d"(a2), "+d"(a3), "+d"(a4), "+d"(a5), "+d"(a6), "+d"(a7)
+                : "d"(x), "d"(y));
+        }
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 0.1234567) sink[0] = s;
+}
 constexpr int kMulIters = 256;
+template <class F>
+__global__ void __launch_bounds__(kThreads) fe_mul_fixed_f64_kernel(uint32_t seed, Fe* sink, const __grid_constant__ FixedMulF64Sel tab) {
+    Fe x[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        x[k] = fe_one<F>();
+        x[k].v[0] ^= (seed + threadIdx.x + k) & 0xffff;
+    }
+#pragma unroll 1
+    for (int i = 0; i < kMulIters; i++) fe_mul_fixed_f64_x2<F>(x[0], x[1], tab.t[(i * seed) >> 30]);  // index: always 0, loop-variant for ptxas
+    Fe s = fe_add<F>(x[0], x[1]);
+    if (s.v[0] == 0x1234567 && s.v[7] == 0x7654321) sink[0] = s;
+}
 template <class F>
 __global__ void __launch_bounds__(kThreads) fe_mul_kernel(uint32_t seed, Fe* sink) {
     Fe x[4], y;
@@ -179,6 +212,23 @@ cudaError_t run_microbench(int field, MicrobenchResult* out, cudaStream_t st) {
         e = time_ms([&] { fe_mul_kernel<Fr377><<<blocks, kThreads, 0, st>>>(7u, (Fe*)sink); }, st, 5, &ms);
     if (e != cudaSuccess) return e;
     out->fe_mul_per_s = threads * kMulIters * 4.0 / (ms * 1e-3);
+    e = time_ms([&] { dfma_kernel<<<blocks, kThreads, 0, st>>>(7u, (double*)sink); }, st, 5, &ms);
+    if (e != cudaSuccess) return e;
+    out->dfma_per_s = threads * kIters * 32.0 / (ms * 1e-3);
+    {
+        host::Field HF(field);
+        host::El r = HF.from_u64(0x123456789abcdefULL);
+        for (int k = 0; k < 5; k++) r = HF.mul(r, HF.add(r, HF.from_u64(77 + k)));  // some dense element
+        FixedMulF64Sel tab;
+        host::fixed_mul_table_f64(HF, r, tab.t[0].t);
+        tab.t[1] = tab.t[0];
+        if (field == Fr381::ID)
+            e = time_ms([&] { fe_mul_fixed_f64_kernel<Fr381><<<blocks, kThreads, 0, st>>>(7u, (Fe*)sink, tab); }, st, 5, &ms);
+        else
+            e = time_ms([&] { fe_mul_fixed_f64_kernel<Fr377><<<blocks, kThreads, 0, st>>>(7u, (Fe*)sink, tab); }, st, 5, &ms);
+        if (e != cudaSuccess) return e;
+        out->fe_mul_fixed_per_s = threads * kMulIters * 2.0 / (ms * 1e-3);
+    }
     // bandwidth: 2 GiB in, 2 GiB out (>> 126 MB L2)
     const uint64_t n = (uint64_t)1 << 26;
     Fe *a = nullptr, *b = nullptr;
