@@ -277,6 +277,7 @@ def run_ours(args):
         local_len = (1 << n) // world
         host_bytes = 32 * local_len  # each rank stages ITS shard (entries rank, rank+world, ...) in pinned host memory
         ptrs = []
+        host_cores = None if os.environ.get("ZK_BENCH_NO_BIND") else zk.bind_host_to_gpu(local_rank)  # pinned buffers next to this GPU's PCIe root
         for k in range(m):
             p = C.c_void_p()
             if lib.zk_host_alloc(host_bytes, C.byref(p)) != 0:
@@ -308,7 +309,9 @@ def run_ours(args):
                 e2e_ms_step = float(tt.item()) / args.steps
                 e2e = {"value": alg_muls(n, m, d) / (e2e_ms_step * 1e-3), "unit": "field-mul/s", "ms_per_step": e2e_ms_step,
                        "h2d_bytes_per_step": 32 * m * local_len * world + 32 * world, "d2h_bytes_per_step": world * (rp.nbytes + ch.nbytes + fin.nbytes),
-                       "api": "zk_sumcheck_prove_host (pinned host tables -> proof on host)"}
+                       "api": "zk_sumcheck_prove_host (pinned host tables -> proof on host)",
+                       "h2d_gbs": (32 * m * local_len * world) / max(e2e_ms_step - ms_per_step, 1e-9) / 1e6,
+                       "host_cores_bound": (len(host_cores) if host_cores else None)}
                 for p in ptrs:
                     lib.zk_host_free(p)
 

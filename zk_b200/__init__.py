@@ -446,3 +446,30 @@ def fft(coefficients, field: int = BLS12_381_FR, ctx: Optional[Context] = None):
 def ifft(evaluations, field: int = BLS12_381_FR, ctx: Optional[Context] = None):
     """fft/src/lib.rs:11-19."""
     return _ntt(evaluations, field, True, ctx)
+
+
+def bind_host_to_gpu(device: int = 0):
+    """Pin the calling process to the CPU cores NVML reports as local to `device` (its PCIe root / NUMA node), so that
+    pinned host buffers allocated afterwards live in memory next to the GPU's PCIe link.  Host-to-device copies of the
+    tables are the whole cost of the host-buffer entry point (`zk_sumcheck_prove_host`), and a buffer on the far socket
+    costs 20-25 % of the PCIe rate.  Returns the list of cores, or None when NVML / the topology is unavailable (then
+    nothing is changed).  Plain deployment hygiene (`numactl --cpunodebind` by hand does the same)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        bus = torch.cuda.get_device_properties(device).pci_bus_id
+        dom = torch.cuda.get_device_properties(device).pci_domain_id
+        dev = torch.cuda.get_device_properties(device).pci_device_id
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (dom, bus, dev)).encode())
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1}
+        use = local & os.sched_getaffinity(0)
+        if not use:
+            return None
+        os.sched_setaffinity(0, use)
+        return sorted(use)
+    except Exception:
+        return None
