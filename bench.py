@@ -252,6 +252,14 @@ def run_ours(args):
     launches = ctx.launch_count() - launches0 - (args.steps - (1 if args.warmup == 0 else 0)) * m  # minus the (untimed) generator launches
     clocks = sampler.stop(wall_t0, wall_t1) if rank == 0 else None
     proof_digest = zk.keccak256(rp.tobytes() + ch.tobytes()).hex()
+    # the CPU oracle's digest of the same full-size proof, committed offline (tests/golden/make_fullsize_digests.py)
+    golden_parity = None
+    try:
+        for c in json.load(open(os.path.join(ROOT, "tests", "golden", "fullsize_digests.json")))["cases"]:
+            if (c["log_n"], c["m"], c["degree"]) == (n, m, d) and int(c["seed"], 16) == SEED:
+                golden_parity = (c["proof_keccak"] == proof_digest)
+    except Exception:
+        pass
     # the reference verifier's own checks on the last proof (host side, sumcheck/src/verifier.rs:44-78):
     # every round check passes, the replayed challenges equal the prover's, and the subclaim equals the
     # product of the fully folded factors
@@ -378,6 +386,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs; IMAD.WIDE products, exact FP64 folds)", "data": "synthetic",
         "config": workload_config(n, m, d, world), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "cpu_baseline": cpu, "prove_ms": ms_per_step, "proof_keccak": proof_digest, "verified": verified,
+        "proof_equals_cpu_oracle_golden": golden_parity,
         "round_kernel_ms": [round(x, 4) for x in ctx.last_round_ms()], "step_ms": [round(x, 3) for x in step_ms], "microbench": mb,
     }
     print(json.dumps(line), flush=True)

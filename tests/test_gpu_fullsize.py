@@ -1,0 +1,44 @@
+"""GPU suite: bit-exact parity at BASELINE's full single-GPU sizes.
+
+tests/golden/fullsize_digests.json holds, for every single-GPU BASELINE workload (2^20 ... 2^26 entries), the Keccak-256 of
+the proof (round polynomials || challenges, Montgomery limbs as they cross the C ABI) and of the final evaluations that
+the CPU oracle produced once, offline, from the same seeded tables (tests/golden/make_fullsize_digests.py, ten minutes
+of CPU).  Here the CUDA path proves the same tables at full size through the C ABI and must reproduce the digests:
+identical round polynomials, challenges and final claims (BASELINE.json north_star) at the sizes the benchmark is
+quoted on, not only at the sizes the oracle finishes in seconds."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+with open(os.path.join(ROOT, "tests", "golden", "fullsize_digests.json")) as f:
+    CASES = json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_fullsize_proof_digest(zk, ctx, case):
+    from zk_b200 import _ffi
+
+    lib = _ffi.lib()
+    n, m, d, seed = case["log_n"], case["m"], case["degree"], int(case["seed"], 16)
+    tabs = [zk.MultiLinearPolynomial.generate(n, k, seed=seed) for k in range(m)]
+    pp = zk.ProductPoly.new(tabs)
+    claim = pp.sum_mont()
+    assert [hex(int(x)) for x in claim] == case["claim_mont_limbs"], "claimed sum differs from the oracle's"
+    rp = np.zeros((n, d + 1, 4), dtype=np.uint64)
+    ch = np.zeros((n, 4), dtype=np.uint64)
+    fin = np.zeros((m, 4), dtype=np.uint64)
+    ctx.check(lib.zk_sumcheck_prove(ctx.h, pp._arr(), m, d, claim.ctypes.data, 0, rp.ctypes.data, ch.ctypes.data, fin.ctypes.data))
+    assert zk.keccak256(rp.tobytes() + ch.tobytes()).hex() == case["proof_keccak"]
+    assert zk.keccak256(fin.tobytes()).hex() == case["finals_keccak"]
+    # and the proof is one the verifier accepts
+    sub = np.zeros(4, dtype=np.uint64)
+    vch = np.zeros((n, 4), dtype=np.uint64)
+    assert lib.zk_sumcheck_verify_partial(0, claim.ctypes.data, rp.ctypes.data, n, d, sub.ctypes.data, vch.ctypes.data) == 0
+    assert (vch == ch).all()
+    del tabs, pp
