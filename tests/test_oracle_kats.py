@@ -256,3 +256,28 @@ def test_field_constants():
         assert (-pow(FF.p, -1, 1 << 32)) % (1 << 32) == 0xFFFFFFFF  # m = -t0 shortcut used by the device multiplier
         assert pow(FF.generator, (FF.p - 1) // 2, FF.p) == FF.p - 1
     assert O.BLS12_381_FR.two_adicity == 32 and O.BLS12_377_FR.two_adicity == 47
+
+
+def test_fullsize_digest_file_is_the_oracles(cref):
+    """tests/golden/fullsize_digests.json (checked by the GPU suite at full size) is reproducible from the C oracle:
+    recompute its 2^20 case here (0.3 s); the larger cases come from the same script (make_fullsize_digests.py)."""
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cases = json.load(open(os.path.join(root, "tests", "golden", "fullsize_digests.json")))["cases"]
+    assert {(c["log_n"], c["m"], c["degree"]) for c in cases} >= {(20, 1, 1), (24, 2, 2), (26, 3, 3)}
+    c = next(c for c in cases if c["log_n"] == 20)
+    seed = int(c["seed"], 16)
+    tabs = [cref.gen_table(0, seed, k, c["log_n"]) for k in range(c["m"])]
+    claim = cref.product_sum(0, tabs, c["log_n"])
+    assert [hex(int(x)) for x in claim] == c["claim_mont_limbs"]
+    rp, ch, fin = cref.prove(0, tabs, c["log_n"], c["degree"], claim, False, fast=True)
+    assert cref.keccak256(rp.tobytes() + ch.tobytes()).hex() == c["proof_keccak"]
+    assert cref.keccak256(fin.tobytes()).hex() == c["finals_keccak"]
+    # the streamlined prover used for the digests is the reference-shaped one, bit for bit (small size)
+    t2 = [cref.gen_table(0, seed, k, 10) for k in range(3)]
+    cl = cref.product_sum(0, t2, 10)
+    a = cref.prove(0, t2, 10, 3, cl, False, fast=True)
+    b = cref.prove(0, t2, 10, 3, cl, False, fast=False)
+    assert all((x == y).all() for x, y in zip(a, b))
