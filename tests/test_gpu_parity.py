@@ -181,6 +181,25 @@ def test_prove_partial_vs_c_oracle(zk, ctx, cref, fid, n, m, d):
     assert prover.final_evals == cref.mont_to_ints(fid, fin)
 
 
+@pytest.mark.parametrize("fid,n,m,d", [(0, 13, 3, 3), (0, 12, 2, 2), (1, 11, 1, 1), (0, 11, 2, 3), (0, 10, 3, 2), (0, 12, 3, 4)])
+def test_prove_with_a_wrong_claimed_sum_vs_c_oracle(zk, ctx, cref, fid, n, m, d):
+    """The round polynomials are computed from the tables, whatever sum the caller claims (prover.rs:42 only absorbs
+    it): a false claim changes the challenges, never the honesty of S_i.  The kernels derive S_i(1) of rounds >= 1 from
+    S_{i-1}(r_{i-1}) — an identity of the tables, not of the claim — so a wrong claim (and D != m) must still match."""
+    refs = [cref.gen_table(fid, 0xD00D, k, n) for k in range(m)]
+    wrong = cref.ints_to_mont(fid, [123456789])[0]
+    rp, ch, fin = cref.prove(fid, refs, n, d, wrong, False, fast=False)
+    pp = zk.ProductPoly.new(gpu_tables(zk, fid, 0xD00D, n, m))
+    prover = zk.SumcheckProver(d)
+    proof, chs = prover.prove_partial(pp, 123456789)
+    assert (proof._round_polys_mont == rp).all()
+    assert chs == cref.mont_to_ints(fid, ch)
+    assert prover.final_evals == cref.mont_to_ints(fid, fin)
+    if d >= m:
+        with pytest.raises(Exception):
+            zk.SumcheckVerifier.verify_partial(proof)  # "verifier check failed: claimed_sum != p(0) + p(1)"
+
+
 def test_zero_variable_and_tiny_products(zk, ctx):
     """n_vars = 0: the prover loop runs zero rounds (`for _ in 0..poly.n_vars()`, prover.rs:44); n = 1: one round."""
     pp = zk.ProductPoly.new([zk.MultiLinearPolynomial.new(0, [5]), zk.MultiLinearPolynomial.new(0, [7])])

@@ -730,6 +730,48 @@ bool perf_log_enabled() {
     return v == 1;
 }
 
+// Value at x of the polynomial of degree < np given by its evaluations ys[t] at t = 0..np-1 (barycentric form, no
+// division by anything that depends on x): the next round's S(0) + S(1), `claimed_sum = p.evaluate(challenge)` in the
+// verifier (sumcheck/src/verifier.rs:68-70).  The inverse denominators 1 / prod_{u != t} (t - u) are cached per field.
+class RoundPolyEvaluator {
+   public:
+    RoundPolyEvaluator(const Field& F, int np) : F_(F), np_(np), w_((size_t)np), pt_((size_t)np) {
+        for (int t = 0; t < np; t++) pt_[(size_t)t] = F.from_u64((uint64_t)t);
+        // the inversions (a field exponentiation each) are done once per thread, field and degree
+        static thread_local std::vector<El> cache[2][ZK_MAX_DEGREE + 2];
+        std::vector<El>& c = cache[F.id()][np];
+        if (c.empty()) {
+            for (int t = 0; t < np; t++) {
+                El den = F.one();
+                for (int u = 0; u < np; u++)
+                    if (u != t) den = F.mul(den, F.sub(pt_[(size_t)t], pt_[(size_t)u]));
+                c.push_back(F.inverse(den));
+            }
+        }
+        w_ = c;
+    }
+    El at(const uint64_t* ys_mont, const El& x) const {
+        std::vector<El> d((size_t)np_), pre((size_t)np_ + 1), suf((size_t)np_ + 1);
+        for (int u = 0; u < np_; u++) d[(size_t)u] = F_.sub(x, pt_[(size_t)u]);
+        pre[0] = F_.one();
+        for (int u = 0; u < np_; u++) pre[(size_t)u + 1] = F_.mul(pre[(size_t)u], d[(size_t)u]);
+        suf[(size_t)np_] = F_.one();
+        for (int u = np_ - 1; u >= 0; u--) suf[(size_t)u] = F_.mul(suf[(size_t)u + 1], d[(size_t)u]);
+        El acc = F_.zero();
+        for (int t = 0; t < np_; t++) {
+            El y;
+            std::memcpy(y.v, ys_mont + 4 * (size_t)t, 32);
+            acc = F_.add(acc, F_.mul(F_.mul(y, w_[(size_t)t]), F_.mul(pre[(size_t)t], suf[(size_t)t + 1])));
+        }
+        return acc;
+    }
+
+   private:
+    const Field& F_;
+    int np_;
+    std::vector<El> w_, pt_;
+};
+
 struct ProveTimer {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     double ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
@@ -797,6 +839,7 @@ int zk_sumcheck_prove(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
     };
 
     std::vector<uint64_t> S((size_t)np * 4);
+    const RoundPolyEvaluator round_eval(F, np);
     size_t ev = 0;
     auto timed = [&](auto&& launch) -> cudaError_t {
         cudaError_t e = cudaEventRecord(ctx->events[ev], ctx->stream);
@@ -849,7 +892,19 @@ int zk_sumcheck_prove(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
             if (st != ZK_OK) { cleanup(); return st; }
             e = timed([&] { next_seq(ctx, sharded); return zk::launch_round_poly(field, cur, (int)m, (int)degree, cur_len / 2, ctx->scratch, ctx->stream, &ctx->launches); });
         } else {
-            e = timed([&] { next_seq(ctx, sharded); return zk::launch_fold_round_poly(field, cur, (int)m, (int)degree, cur_len, rf, ctx->scratch, ctx->stream, &ctx->launches); });
+            // S_{round+1}(0) + S_{round+1}(1) = S_round(r): the kernel skips the t = 1 term and derives it (sharded:
+            // the map is linear, so the value goes to rank 0 and zero to the others before the all-reduce).
+            // Only when the D+1 evaluations determine the round polynomial, i.e. D >= m: the reference does not
+            // validate MAX_VAR_DEGREE against the factor count (prover.rs:48-56), and with D < m the interpolant
+            // through S(0..D) is not the true polynomial, so there the t = 1 term is computed like the others.
+            const bool derive_s1 = degree >= 1 && degree >= m;
+            Fe claim_next = Fe{};
+            if (derive_s1 && (!sharded || ctx->rank == 0)) {
+                const El c = round_eval.at(S.data(), r);
+                std::memcpy(claim_next.v, c.v, 32);
+            }
+            const Fe* claim_ptr = derive_s1 ? &claim_next : nullptr;
+            e = timed([&] { next_seq(ctx, sharded); return zk::launch_fold_round_poly(field, cur, (int)m, (int)degree, cur_len, rf, ctx->scratch, ctx->stream, &ctx->launches, claim_ptr); });
             cur_len /= 2;
         }
         if (e != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "fold_round_poly"); }

@@ -44,8 +44,11 @@ cudaError_t launch_fold(int field, const TablePtrs& tabs, int m, uint64_t half, 
                         int* launches);
 // Fused: fold the n_prev-entry tables at r (halving them in place), and in the same pass produce the
 // next round's polynomial over the folded tables.  n_prev >= 4.
+// `claim` (optional, fused path only): this rank's share of S_prev(r) — the value S(0) + S(1) of the round being
+// computed must have — lets the kernel skip the t = 1 term and publish S(1) = claim - S(0) (same field element).
 cudaError_t launch_fold_round_poly(int field, const TablePtrs& tabs, int m, int degree, uint64_t n_prev, const Fe& r,
-                                   const ReduceScratch& scratch, cudaStream_t stream, int* launches);
+                                   const ReduceScratch& scratch, cudaStream_t stream, int* launches,
+                                   const Fe* claim = nullptr);
 // sum_j prod_k A_k[j]  (the claim): result in scratch.result_dev[0] / result_host[0].
 cudaError_t launch_product_sum(int field, const TablePtrs& tabs, int m, uint64_t n, const ReduceScratch& scratch,
                                cudaStream_t stream, int* launches);

@@ -71,6 +71,11 @@ struct ReduceArgs {
     unsigned* flag_host;  // mapped pinned word the host spins on (saves a stream synchronisation per round)
     unsigned seq;
     uint64_t* lanes;      // sharded runs: one 32-bit limb per u64 lane, the input of the exact ncclSum all-reduce
+    // Rounds >= 1 of a proof: S(0) + S(1) equals the previous round polynomial at its challenge — an identity of the
+    // tables, whatever sum the caller claimed — so the kernel skips the products of the t = 1 term and the last block
+    // publishes S(1) = claim - S(0): the same field element (prover.rs:49-56 computes it directly).
+    int skip1;
+    Fe claim;             // this rank's share of S_prev(r_prev): the value on rank 0, zero elsewhere (the map is linear)
 };
 constexpr int kWorkCounterOffset = 32;  // the work counter lives 128 bytes after the ticket (own cache line)
 
@@ -159,6 +164,7 @@ __device__ __forceinline__ void reduce_publish(Fe* acc, const ReduceArgs& ra) {
         Fe fin[NP];
 #pragma unroll
         for (int t = 0; t < NP; t++) fin[t] = s_fin[t];
+        if (ra.skip1 && NP > 1) fin[1] = fe_sub<F>(ra.claim, fin[0]);
         if (TOOM) toom_to_evals<F>(fin);
 #pragma unroll
         for (int t = 0; t < NP; t++) {
@@ -249,7 +255,7 @@ __device__ __forceinline__ Fe accw_reduce(const Accw& a) {
 // values, so its value at -1 is 2(A(0) + A(inf)) - A(1): one multiplication less per item (7 instead of 8).
 // The four sums are mapped back to S(0..3) by exact field arithmetic in the last block (toom_to_evals).
 template <class F, int D, bool TOOM>
-__device__ __forceinline__ void item_terms(int k, bool last, Fe lo, Fe hi, Fe* pr, const Accw& accw) {
+__device__ __forceinline__ void item_terms(int k, bool last, bool skip1, Fe lo, Fe hi, Fe* pr, const Accw& accw) {
     if (TOOM) {  // pr[0..3] live at t = 0, 1, -1, inf ; m == 3
         const Fe d = fe_sub<F>(hi, lo);
         if (k == 0) {
@@ -263,7 +269,7 @@ __device__ __forceinline__ void item_terms(int k, bool last, Fe lo, Fe hi, Fe* p
         } else {
             uint32_t w[16];
             fe_mul_wide(w, lo, pr[0]); accw_add16(accw, w);
-            fe_mul_wide(w, hi, pr[1]); accw_add16(accw_at(accw, 1), w);
+            if (!skip1) { fe_mul_wide(w, hi, pr[1]); accw_add16(accw_at(accw, 1), w); }
             fe_mul_wide(w, fe_sub<F>(lo, d), pr[2]); accw_add16(accw_at(accw, 2), w);
             fe_mul_wide(w, d, pr[3]); accw_add16(accw_at(accw, 3), w);
         }
@@ -280,14 +286,19 @@ __device__ __forceinline__ void item_terms(int k, bool last, Fe lo, Fe hi, Fe* p
         }
         if (last) {  // m == 1: the terms are the table values themselves
 #pragma unroll
-            for (int t = 0; t <= D; t++) accw_add_hi(accw_at(accw, t), pr[t]);
+            for (int t = 0; t <= D; t++)
+                if (!(skip1 && t == 1)) accw_add_hi(accw_at(accw, t), pr[t]);
         }
     } else {
         uint32_t w[16];
         if (last) { fe_mul_wide(w, lo, pr[0]); accw_add16(accw, w); } else pr[0] = fe_mul<F>(lo, pr[0]);
         if (D >= 2) lo = fe_sub<F>(hi, lo);  // lo := d
         if (D >= 1) {
-            if (last) { fe_mul_wide(w, hi, pr[1]); accw_add16(accw_at(accw, 1), w); } else pr[1] = fe_mul<F>(hi, pr[1]);
+            if (last) {
+                if (!skip1) { fe_mul_wide(w, hi, pr[1]); accw_add16(accw_at(accw, 1), w); }
+            } else {
+                pr[1] = fe_mul<F>(hi, pr[1]);
+            }
         }
 #pragma unroll
         for (int t = 2; t <= D; t++) {
@@ -420,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? (FOLD ? ZK_RK_MINBLOCKS_D
                         n1 = ld_fe_stream(NT + nj + q);
                     }
                 }
-                item_terms<F, D, TOOM>(k, k == m - 1, lo, hi, pr, accw);
+                item_terms<F, D, TOOM>(k, k == m - 1, FOLD && ra.skip1 != 0, lo, hi, pr, accw);
             }
         }
         wc.advance();
@@ -501,7 +512,7 @@ inline bool dynamic_chunks() {
     return on;
 }
 inline ReduceArgs make_ra(const ReduceScratch& s, int slot) {
-    return ReduceArgs{s.block_partials, s.ticket, s.result_dev, s.result_host_devptr, slot, s.flag_host_devptr, s.seq, s.lanes};
+    return ReduceArgs{s.block_partials, s.ticket, s.result_dev, s.result_host_devptr, slot, s.flag_host_devptr, s.seq, s.lanes, 0, Fe{}};
 }
 template <class F>
 Fe small_constant(unsigned t);  // Montgomery form of small integer t (host side)
@@ -540,7 +551,7 @@ inline bool fold_on_f64(int m) {
 }
 
 template <class F, int D, bool FOLD, bool TOOM, bool F64, bool DYN>
-cudaError_t do_round_v(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st) {
+cudaError_t do_round_v(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st, const Fe* claim) {
     const FixedMul tab = (FOLD && !F64) ? make_fixed<F>(r) : FixedMul{};
     const FixedMulF64Sel tab64 = F64 ? make_fixed_f64<F>(r) : FixedMulF64Sel{};
     constexpr size_t smem = accw_bytes(D + 1);
@@ -551,24 +562,29 @@ cudaError_t do_round_v(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, co
         return nb;
     }();
     unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
-    round_kernel<F, D, FOLD, TOOM, F64, DYN><<<grid, kThreads, smem, st>>>(tabs, m, q, tab, tab64, make_ra(s, 0));
+    ReduceArgs ra = make_ra(s, 0);
+    if (FOLD && claim && D >= 1) {
+        ra.skip1 = 1;
+        ra.claim = *claim;
+    }
+    round_kernel<F, D, FOLD, TOOM, F64, DYN><<<grid, kThreads, smem, st>>>(tabs, m, q, tab, tab64, ra);
     return cudaGetLastError();
 }
 template <class F, int D, bool FOLD, bool TOOM = false>
-cudaError_t do_round(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st) {
+cudaError_t do_round(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st, const Fe* claim) {
     const bool dyn = m >= 2 && dynamic_chunks();
     if (FOLD && fold_on_f64(m))
-        return dyn ? do_round_v<F, D, FOLD, TOOM, FOLD, true>(tabs, m, q, r, s, st) : do_round_v<F, D, FOLD, TOOM, FOLD, false>(tabs, m, q, r, s, st);
-    return dyn ? do_round_v<F, D, FOLD, TOOM, false, true>(tabs, m, q, r, s, st) : do_round_v<F, D, FOLD, TOOM, false, false>(tabs, m, q, r, s, st);
+        return dyn ? do_round_v<F, D, FOLD, TOOM, FOLD, true>(tabs, m, q, r, s, st, claim) : do_round_v<F, D, FOLD, TOOM, FOLD, false>(tabs, m, q, r, s, st, claim);
+    return dyn ? do_round_v<F, D, FOLD, TOOM, false, true>(tabs, m, q, r, s, st, claim) : do_round_v<F, D, FOLD, TOOM, false, false>(tabs, m, q, r, s, st, claim);
 }
 template <class F, bool FOLD>
 cudaError_t do_round_deg(const TablePtrs& tabs, int m, int degree, uint64_t q, const Fe& r, const ReduceScratch& s,
-                         cudaStream_t st) {
+                         cudaStream_t st, const Fe* claim = nullptr) {
     switch (degree) {
-        case 1: return do_round<F, 1, FOLD>(tabs, m, q, r, s, st);
-        case 2: return do_round<F, 2, FOLD>(tabs, m, q, r, s, st);
-        case 3: return m == 3 ? do_round<F, 3, FOLD, true>(tabs, m, q, r, s, st) : do_round<F, 3, FOLD>(tabs, m, q, r, s, st);
-        case 4: return do_round<F, 4, FOLD>(tabs, m, q, r, s, st);
+        case 1: return do_round<F, 1, FOLD>(tabs, m, q, r, s, st, claim);
+        case 2: return do_round<F, 2, FOLD>(tabs, m, q, r, s, st, claim);
+        case 3: return m == 3 ? do_round<F, 3, FOLD, true>(tabs, m, q, r, s, st, claim) : do_round<F, 3, FOLD>(tabs, m, q, r, s, st, claim);
+        case 4: return do_round<F, 4, FOLD>(tabs, m, q, r, s, st, claim);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -620,9 +636,9 @@ cudaError_t fold_dispatch(const TablePtrs& tabs, int m, uint64_t half, const Fe&
 }
 template <class F>
 cudaError_t fold_round_poly_dispatch(const TablePtrs& tabs, int m, int degree, uint64_t n_prev, const Fe& r,
-                                     const ReduceScratch& s, cudaStream_t st, int* launches) {
+                                     const ReduceScratch& s, cudaStream_t st, int* launches, const Fe* claim) {
     const uint64_t q = n_prev / 4;
-    if (has_fused_path(m, degree)) { ++*launches; return do_round_deg<F, true>(tabs, m, degree, q, r, s, st); }
+    if (has_fused_path(m, degree)) { ++*launches; return do_round_deg<F, true>(tabs, m, degree, q, r, s, st, claim); }
     cudaError_t e = fold_dispatch<F>(tabs, m, n_prev / 2, r, &s, st, launches);
     if (e != cudaSuccess) return e;
     return round_poly_dispatch<F>(tabs, m, degree, n_prev / 4, s, st, launches);
@@ -652,9 +668,9 @@ cudaError_t launch_fold(int field, const TablePtrs& tabs, int m, uint64_t half, 
                               : fold_dispatch<Fr377>(tabs, m, half, r, nullptr, stream, launches);
 }
 cudaError_t launch_fold_round_poly(int field, const TablePtrs& tabs, int m, int degree, uint64_t n_prev, const Fe& r,
-                                   const ReduceScratch& scratch, cudaStream_t stream, int* launches) {
-    return field == Fr381::ID ? fold_round_poly_dispatch<Fr381>(tabs, m, degree, n_prev, r, scratch, stream, launches)
-                              : fold_round_poly_dispatch<Fr377>(tabs, m, degree, n_prev, r, scratch, stream, launches);
+                                   const ReduceScratch& scratch, cudaStream_t stream, int* launches, const Fe* claim) {
+    return field == Fr381::ID ? fold_round_poly_dispatch<Fr381>(tabs, m, degree, n_prev, r, scratch, stream, launches, claim)
+                              : fold_round_poly_dispatch<Fr377>(tabs, m, degree, n_prev, r, scratch, stream, launches, claim);
 }
 cudaError_t launch_product_sum(int field, const TablePtrs& tabs, int m, uint64_t n, const ReduceScratch& scratch,
                                cudaStream_t stream, int* launches) {
