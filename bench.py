@@ -339,12 +339,14 @@ def run_ours(args):
     # product is 112 IMAD.WIDE.U32, the last product of a term 64 (unreduced); the cubic/3-factor case carries its
     # terms at the Toom points (3 intermediate products instead of 4).  Folds: with two or more factors they run on
     # the FP64 pipe (field_f64.cuh: 128 DFMA + 6 IMAD.WIDE each), a single table folds on the integer pipe (76).
+    # Rounds >= 1 with D >= m derive S(1) from the previous round polynomial: one unreduced product less per item.
+    last_terms = d if d >= m else d + 1
     if m == 1:
         prod_wide = 0
     elif m == 3 and d == 3:
-        prod_wide = 3 * 112 + 4 * 64
+        prod_wide = 3 * 112 + last_terms * 64
     else:
-        prod_wide = (m - 2) * (d + 1) * 112 + (d + 1) * 64
+        prod_wide = (m - 2) * (d + 1) * 112 + last_terms * 64
     fold_pipe = os.environ.get("ZK_B200_FOLD_PIPE", "f64" if m >= 2 else "int")[0]
     fold_wide, fold_dfma = (6, 128) if fold_pipe == "f" else (76, 0)
     wide_per_item = 2 * m * fold_wide + prod_wide
