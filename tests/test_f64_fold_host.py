@@ -18,3 +18,17 @@ def test_f64_fold_matches_host_multiplier(tmp_path):
     out = subprocess.run([exe], check=True, capture_output=True, timeout=300, text=True).stdout
     assert "0 mismatches" in out, out
     assert "4800000 checked" in out, out
+
+
+def test_keccak_avx512_matches_portable(tmp_path):
+    """The AVX-512 absorb loop of the host transcript (zk_b200/csrc/keccak_avx512.cpp) against the portable
+    Keccak-f[1600] of keccak.hpp: KATs, every length 0..1100 in six chunkings, large messages, digest chaining.
+    (Prints "skipped" and passes on a CPU without AVX-512.)"""
+    obj, exe = str(tmp_path / "keccak_avx512.o"), str(tmp_path / "test_keccak_avx512")
+    src = os.path.join(ROOT, "zk_b200", "csrc")
+    subprocess.run(["g++", "-std=c++17", "-O3", "-mavx512f", "-mavx512vl", "-c", os.path.join(src, "keccak_avx512.cpp"), "-o", obj],
+                   check=True, capture_output=True, timeout=300)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I", src, os.path.join(ROOT, "tests", "cpp", "test_keccak_avx512.cpp"), obj, "-o", exe],
+                   check=True, capture_output=True, timeout=300)
+    out = subprocess.run([exe], check=True, capture_output=True, timeout=600, text=True).stdout
+    assert "skipped" in out or "0 mismatches" in out, out
