@@ -19,6 +19,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 
 namespace {
 
@@ -102,7 +103,11 @@ extern "C" {
 
 // 1 when the CPU executes AVX-512F/VL (the OS-enabled state is part of the builtin's check)
 __attribute__((visibility("hidden"))) int zk_keccak_avx512_available() {
-    static const int ok = (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl")) ? 1 : 0;
+    static const int ok = [] {
+        const char* e = std::getenv("ZK_B200_KECCAK");  // "portable" pins the scalar permutation (A/B measurements)
+        if (e && e[0] == 'p') return 0;
+        return (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl")) ? 1 : 0;
+    }();
     return ok;
 }
 
