@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# ZK_B200_LIB: tuning builds of the same library (scripts/gpu_ab2.sh); default = the in-tree product build
+# ZK_B200_LIB: tuning builds of the same library (scripts/gpu_ab.sh); default = the in-tree product build
 SO_PATH = os.environ.get("ZK_B200_LIB") or os.path.join(_HERE, "libzk_b200.so")
 
 u64p = C.POINTER(C.c_uint64)
