@@ -153,7 +153,10 @@ ZK_API int zk_sumcheck_prove(zk_ctx* ctx, zk_table* const* tables, unsigned m, u
 /* Same with HOST tables (each 2^n_vars elements): upload + (optional) claim + prove in one call — the
  * end-to-end entry a caller holding `Vec<Fr>`s uses.  If `sum` is NULL the claim is computed on the device
  * (zk_product_sum) and returned in sum_out.  On a sharded ctx each rank passes ITS shard (entries rank,
- * rank+world, ... stored densely, 2^n_vars / world elements) — no rank needs the whole table in host memory. */
+ * rank+world, ... stored densely, 2^n_vars / world elements) — no rank needs the whole table in host memory.
+ * The device landing buffers (m tables) stay with the context between calls, grow-only, and are released by
+ * zk_ctx_destroy: a proof per call then costs the uploads and the rounds, not a cudaMalloc/cudaFree of gigabytes.
+ * Host tables should be pinned (zk_host_alloc); the uploads run on two copy streams. */
 ZK_API int zk_sumcheck_prove_host(zk_ctx* ctx, int field, const uint64_t* const* host_tables, unsigned m, unsigned n_vars,
                            unsigned degree, const uint64_t* sum, int absorb_initial_poly, uint64_t* round_polys_out,
                            uint64_t* challenges_out, uint64_t* final_evals_out, uint64_t sum_out[4]);

@@ -81,6 +81,10 @@ struct zk_ctx {
     size_t eval_cap = 0;                  // elements
     std::vector<cudaStream_t> copy_streams;  // extra H2D streams of zk_sumcheck_prove_host (lazily created)
     cudaEvent_t copy_done = nullptr;
+    // device landing buffers of zk_sumcheck_prove_host, kept between calls (grow-only): a cudaMalloc + cudaFree of
+    // gigabytes per proof is milliseconds of the host-buffer path and a device-wide synchronisation
+    std::vector<Fe*> host_prove_buf;
+    std::vector<size_t> host_prove_cap;  // elements
 };
 
 struct zk_table {
@@ -333,6 +337,7 @@ void zk_ctx_destroy(zk_ctx* c) {
     cudaFreeHost(c->scratch.result_host);
     cudaFreeHost(c->scratch.flag_host);
     cudaFree(c->lanes);
+    for (Fe* b : c->host_prove_buf) cudaFree(b);
     for (cudaStream_t s : c->copy_streams) cudaStreamDestroy(s);
     if (c->copy_done) cudaEventDestroy(c->copy_done);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -948,7 +953,7 @@ int zk_sumcheck_prove_host(zk_ctx* ctx, int field, const uint64_t* const* host_t
     if (n_vars >= 40) return fail(ctx, ZK_ERR_INVALID_ARG);
     CU(ctx, cudaSetDevice(ctx->device));
     std::vector<zk_table*> tabs(m, nullptr);
-    auto free_all = [&]() { for (auto t : tabs) zk_table_free(t); };
+    auto free_all = [&]() { for (auto t : tabs) delete t; };  // the device memory stays in ctx->host_prove_buf
     const uint64_t len = (uint64_t)1 << n_vars, world = (uint64_t)ctx->world;
     if (world > 1 && len < world) return fail(ctx, ZK_ERR_UNSUPPORTED, "table smaller than the number of ranks");
     int st = ZK_OK;
@@ -970,8 +975,17 @@ int zk_sumcheck_prove_host(zk_ctx* ctx, int field, const uint64_t* const* host_t
     const uint64_t local_len = len / world;
     for (unsigned k = 0; k < m && st == ZK_OK; k++) {
         if (!host_tables[k]) { st = fail(ctx, ZK_ERR_INVALID_ARG, "null table"); break; }
-        st = table_alloc(ctx, field, n_vars, local_len, &tabs[k]);
-        if (st != ZK_OK) break;
+        if (ctx->host_prove_buf.size() <= k) { ctx->host_prove_buf.push_back(nullptr); ctx->host_prove_cap.push_back(0); }
+        if (ctx->host_prove_cap[k] < local_len) {
+            cudaFree(ctx->host_prove_buf[k]);
+            ctx->host_prove_buf[k] = nullptr;
+            ctx->host_prove_cap[k] = 0;
+            cudaError_t ea = cudaMalloc((void**)&ctx->host_prove_buf[k], (size_t)local_len * sizeof(Fe));
+            if (ea != cudaSuccess) { cudaGetLastError(); st = cuda_fail(ctx, ea, "cudaMalloc(table)"); break; }
+            ctx->host_prove_cap[k] = (size_t)local_len;
+        }
+        tabs[k] = new (std::nothrow) zk_table{ctx, field, n_vars, local_len, ctx->host_prove_buf[k], ctx->host_prove_cap[k]};
+        if (!tabs[k]) { st = fail(ctx, ZK_ERR_OOM); break; }
         cudaError_t e = cudaSuccess;
         if (n_copy == 1 || local_len < (uint64_t)n_copy * 4096) {
             e = cudaMemcpyAsync(tabs[k]->data, host_tables[k], (size_t)local_len * 32, cudaMemcpyHostToDevice, ctx->stream);
