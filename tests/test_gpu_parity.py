@@ -253,21 +253,22 @@ def test_config1_prove_verify_2p20(zk, ctx, cref):
 
 
 def test_prove_host_buffers_e2e(zk, ctx, cref):
-    """zk_sumcheck_prove_host: host tables in, proof out (the end-to-end entry bench.py times)."""
+    """zk_sumcheck_prove_host: host tables in, proof out (the end-to-end entry bench.py times).  The device landing
+    buffers stay with the context between calls: grow, shrink, more and fewer factors, in sequence."""
     import ctypes as C
 
     from zk_b200 import _ffi
 
-    n, m, d = 15, 3, 3
-    refs = [cref.gen_table(0, 5, k, n) for k in range(m)]
-    claim = cref.product_sum(0, refs, n)
-    rp, ch, fin = cref.prove(0, refs, n, d, claim, False, fast=True)
-    arr = (C.c_void_p * m)(*[r.ctypes.data for r in refs])
-    rp_g = np.zeros_like(rp); ch_g = np.zeros_like(ch); fin_g = np.zeros_like(fin); sum_g = np.zeros(4, dtype=np.uint64)
-    st = _ffi.lib().zk_sumcheck_prove_host(ctx.h, 0, arr, m, n, d, None, 0, rp_g.ctypes.data, ch_g.ctypes.data,
-                                           fin_g.ctypes.data, sum_g.ctypes.data)
-    assert st == 0
-    assert (sum_g == claim).all() and (rp_g == rp).all() and (ch_g == ch).all() and (fin_g == fin).all()
+    for n, m, d in [(15, 3, 3), (17, 2, 2), (12, 3, 3), (17, 4, 4), (9, 1, 1), (15, 3, 3)]:
+        refs = [cref.gen_table(0, 5 + n, k, n) for k in range(m)]
+        claim = cref.product_sum(0, refs, n)
+        rp, ch, fin = cref.prove(0, refs, n, d, claim, False, fast=True)
+        arr = (C.c_void_p * m)(*[r.ctypes.data for r in refs])
+        rp_g = np.zeros_like(rp); ch_g = np.zeros_like(ch); fin_g = np.zeros_like(fin); sum_g = np.zeros(4, dtype=np.uint64)
+        st = _ffi.lib().zk_sumcheck_prove_host(ctx.h, 0, arr, m, n, d, None, 0, rp_g.ctypes.data, ch_g.ctypes.data,
+                                               fin_g.ctypes.data, sum_g.ctypes.data)
+        assert st == 0, (n, m, d)
+        assert (sum_g == claim).all() and (rp_g == rp).all() and (ch_g == ch).all() and (fin_g == fin).all(), (n, m, d)
 
 
 # ---- properties at sizes the oracle does not reach ------------------------------------------------------------------
