@@ -2,7 +2,10 @@
 `gloo`.  Two processes each hold the strided shard (index = rank mod world) of seeded tables, compute their
 partial round polynomials with the oracle's field arithmetic, all-reduce them as 32-bit limbs widened into
 64-bit lanes (the exact trick the CUDA path uses with ncclSum), hash redundantly, fold locally, and gather +
-re-interleave the residual.  The transcript must equal the single-process oracle's.  This checks the host-side
+re-interleave the residual.  In rounds >= 1 (and D >= m) each rank skips the t = 1 term and publishes
+claim_share - S(0) instead, where the share of S_prev(r_prev) is the whole value on rank 0 and zero elsewhere — the
+rule the CUDA path uses (api.cu, `derive_s1`); the all-reduce restores S(1).  The transcript must equal the
+single-process oracle's.  This checks the host-side
 logic of the N > 1 path (shard axis, lane all-reduce exactness, residual interleave); the kernels themselves
 are covered by tests/dist_parity.py on real GPUs."""
 import os
@@ -52,10 +55,24 @@ def _worker(rank, world, port, n, m, d, gather_at, out):
             res.append(acc % p)  # carry-propagate + reduce
         return res
 
-    def round_poly(tables):
+    def lagrange_at(ys, x):  # value at x of the polynomial through (t, ys[t]), t = 0..len-1
+        acc = 0
+        for t, y in enumerate(ys):
+            num, den = 1, 1
+            for u in range(len(ys)):
+                if u != t:
+                    num = num * (x - u) % p
+                    den = den * (t - u) % p
+            acc = (acc + y * num * pow(den, p - 2, p)) % p
+        return acc
+
+    def round_poly(tables, claim_share=None):
         half = len(tables[0]) // 2
         S = []
         for t in range(d + 1):
+            if t == 1 and claim_share is not None:  # derived: this rank's share of the claim minus its S(0)
+                S.append((claim_share - S[0]) % p)
+                continue
             acc = 0
             for j in range(half):
                 pr = 1
@@ -79,7 +96,11 @@ def _worker(rank, world, port, n, m, d, gather_at, out):
                 L = len(T)
                 full.append([gathered[g % world][g // world] for g in range(L * world)])
             cur, sharded = full, False
-        S = round_poly(cur)
+        share = None
+        if rnd >= 1 and d >= m and d >= 1:
+            prev_at_r = lagrange_at(rps[-1], chs[-1])
+            share = prev_at_r if (not sharded or rank == 0) else 0
+        S = round_poly(cur, share)
         if sharded:
             S = allreduce_elems(S)
         rps.append(S)
