@@ -204,6 +204,11 @@ ZK_API int zk_field_add(int field, const uint64_t a[4], const uint64_t b[4], uin
 ZK_API int zk_field_sub(int field, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]);
 ZK_API int zk_field_inverse(int field, const uint64_t a[4], uint64_t out[4]); /* ZK_ERR_INVALID_ARG for zero */
 ZK_API int zk_field_root_of_unity(int field, uint64_t n, uint64_t out[4]);    /* get_root_of_unity; ZK_ERR_NO_ROOT */
+/* Value at x of the polynomial of degree < n_points given by its evaluations at 0..n_points-1:
+ * `UnivariatePolynomial::interpolate(xs = 0.., ys).evaluate(x)` (polynomial/src/univariate_poly.rs:29-80), what the
+ * verifier computes as the next claimed sum (sumcheck/src/verifier.rs:68-70) and what the prover uses to derive
+ * S_i(1) = S_{i-1}(r_{i-1}) - S_i(0) in rounds >= 1.  Host only; n_points in 1..ZK_MAX_DEGREE+1. */
+ZK_API int zk_round_poly_evaluate(int field, const uint64_t* ys, unsigned n_points, const uint64_t x[4], uint64_t out[4]);
 
 /* ---- measurement support ---------------------------------------------------------------------- */
 typedef struct zk_microbench {

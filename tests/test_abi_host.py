@@ -168,3 +168,26 @@ def test_proof_dump_layout(zk, golden):
     assert proof.to_bytes() == exp
     exp_full = exp + b"".join(F.to_bytes_be(x) for x in chs) + b"".join(F.to_bytes_be(x) for x in fins)
     assert proof.to_bytes(chs, fins) == exp_full
+
+
+@pytest.mark.parametrize("fid", [0, 1])
+def test_round_poly_evaluate_vs_oracle(zk, fid):
+    """zk_round_poly_evaluate == UnivariatePolynomial::interpolate(ys).evaluate(x) (univariate_poly.rs:29-80): the value
+    the verifier takes as the next claimed sum and the prover uses to derive S(1) of the next round."""
+    from zk_b200 import _ffi
+
+    lib = _ffi.lib()
+    FF = O.FIELDS[fid]
+    rng = np.random.default_rng(11 + fid)
+    for npts in (1, 2, 3, 4, 5, 9, 16):
+        for trial in range(4):
+            ys = [int.from_bytes(rng.bytes(32), "little") % FF.p for _ in range(npts)]
+            xs = [int.from_bytes(rng.bytes(32), "little") % FF.p, 0, npts - 1, FF.p - 1][trial]
+            want = O.UnivariatePolynomial.interpolate(FF, ys).evaluate(xs)
+            ym, xm, out = zk.to_mont(fid, ys), zk.to_mont(fid, [xs]), np.zeros(4, dtype=np.uint64)
+            assert lib.zk_round_poly_evaluate(fid, ym.ctypes.data, npts, xm.ctypes.data, out.ctypes.data) == 0
+            assert zk.from_mont(fid, out)[0] == want, (npts, trial)
+    out = np.zeros(4, dtype=np.uint64)
+    one = zk.to_mont(fid, [1])
+    assert lib.zk_round_poly_evaluate(fid, one.ctypes.data, 0, one.ctypes.data, out.ctypes.data) != 0
+    assert lib.zk_round_poly_evaluate(fid, one.ctypes.data, 17, one.ctypes.data, out.ctypes.data) != 0

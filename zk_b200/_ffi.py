@@ -88,6 +88,7 @@ SIGNATURES = {
     "zk_field_sub": (C.c_int, [C.c_int, vp, vp, vp]),
     "zk_field_inverse": (C.c_int, [C.c_int, vp, vp]),
     "zk_field_root_of_unity": (C.c_int, [C.c_int, C.c_uint64, vp]),
+    "zk_round_poly_evaluate": (C.c_int, [C.c_int, vp, C.c_uint, vp, vp]),
     "zk_microbench_run": (C.c_int, [vp, C.c_int, C.POINTER(zk_microbench)]),
 }
 

@@ -1274,6 +1274,18 @@ int zk_field_root_of_unity(int field, uint64_t n, uint64_t out[4]) {
     return ZK_OK;
 }
 
+int zk_round_poly_evaluate(int field, const uint64_t* ys, unsigned n_points, const uint64_t x[4], uint64_t out[4]) {
+    if (!valid_field(field) || !ys || !x || !out || n_points == 0 || n_points > ZK_MAX_DEGREE + 1) return ZK_ERR_INVALID_ARG;
+    const Field F(field);
+    for (unsigned t = 0; t < n_points; t++)
+        if (!F.is_canonical(el_from(ys + 4 * (size_t)t))) return ZK_ERR_INVALID_ARG;
+    if (!F.is_canonical(el_from(x))) return ZK_ERR_INVALID_ARG;
+    const RoundPolyEvaluator ev(F, (int)n_points);
+    const El r = ev.at(ys, el_from(x));
+    std::memcpy(out, r.v, 32);
+    return ZK_OK;
+}
+
 int zk_microbench_run(zk_ctx* ctx, int field, zk_microbench* out) {
     if (!ctx || !out || !valid_field(field)) return fail(ctx, ZK_ERR_INVALID_ARG);
     CU(ctx, cudaSetDevice(ctx->device));
