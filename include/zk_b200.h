@@ -178,6 +178,40 @@ ZK_API int zk_sumcheck_proof_dump(int field, const uint64_t sum[4], const uint64
                            unsigned degree, const uint64_t* challenges, const uint64_t* final_evals, unsigned m,
                            uint8_t* out, size_t out_cap, size_t* out_len, uint8_t digest_out[32]);
 
+/* ---- sum of products ---------------------------------------------------------------
+ * P(x) = sum_t prod_{k in term t} A_k(x) over n_tables distinct tables — the shape of a GKR layer polynomial
+ * add.(Wb + Wc) + mul.Wb.Wc = add.Wb + add.Wc + mul.Wb.Wc, the caller readme.md:9 names.  The reference itself stops at a
+ * single product (ProductPoly, polynomial/src/product_poly.rs:4-10), so there is no reference item behind these entry
+ * points; the protocol is the reference's prover loop unchanged (sumcheck/src/prover.rs:33-73: append the sum, per round
+ * the evaluations at t = 0..degree, a Keccak challenge, fold every table at it), and a single-term sum produces
+ * bit-for-bit the ProductPoly proof.  Terms are given as `term_len[t]` factor counts (1..ZK_MAX_FACTORS) and the
+ * concatenated `term_factors` (indices into tables[]); at most ZK_MAX_TERMS terms; a table may appear in several terms
+ * or several times in one, but only once in tables[].  `degree` (MAX_VAR_DEGREE) must be 1..4 and, as in the
+ * reference, is not validated against the longest term. */
+#define ZK_MAX_TERMS 8
+/* Evaluations at t = 0..degree of sum_x P(t, x): one round polynomial (prover.rs:48-56 for the sum of products). */
+ZK_API int zk_sop_round_poly(zk_ctx* ctx, const zk_table* const* tables, unsigned n_tables, const uint8_t* term_len,
+                             const uint8_t* term_factors, unsigned n_terms, unsigned degree, uint64_t* out);
+/* sum over the hypercube of P: the honest claim. */
+ZK_API int zk_sop_sum(zk_ctx* ctx, const zk_table* const* tables, unsigned n_tables, const uint8_t* term_len,
+                      const uint8_t* term_factors, unsigned n_terms, uint64_t out[4]);
+/* P(point): every table evaluated on the device (evaluation_form.rs:83-89), combined on the host — the verifier's
+ * final check against SubClaim.sum (verifier.rs:28-32).  ZK_ERR_EVALUATE_ARITY unless len == n_vars. */
+ZK_API int zk_sop_evaluate(zk_ctx* ctx, const zk_table* const* tables, unsigned n_tables, const uint8_t* term_len,
+                           const uint8_t* term_factors, unsigned n_terms, const uint64_t* point, unsigned len,
+                           uint64_t out[4]);
+/* Host only: sum_t prod_k table_values[term_factors..] — P at a point from the n_tables table values there (e.g. the
+ * prover's final evaluations). */
+ZK_API int zk_sop_combine(int field, const uint8_t* term_len, const uint8_t* term_factors, unsigned n_terms,
+                          const uint64_t* table_values, unsigned n_tables, uint64_t out[4]);
+/* The prover over the sum of products; arguments as zk_sumcheck_prove (absorb_initial_poly absorbs the tables'
+ * to_bytes() in tables[] order first).  CONSUMES the tables.  final_evals_out: n_tables elements.  Works on sharded
+ * contexts like zk_sumcheck_prove (absorb_initial_poly == 0 there). */
+ZK_API int zk_sumcheck_prove_sop(zk_ctx* ctx, zk_table* const* tables, unsigned n_tables, const uint8_t* term_len,
+                                 const uint8_t* term_factors, unsigned n_terms, unsigned degree, const uint64_t sum[4],
+                                 int absorb_initial_poly, uint64_t* round_polys_out, uint64_t* challenges_out,
+                                 uint64_t* final_evals_out);
+
 /* ---- transcript  (transcript/src/lib.rs) — host Keccak-256 -------------------------------------- */
 ZK_API zk_transcript* zk_transcript_new(void);                                             /* :10 */
 ZK_API void zk_transcript_free(zk_transcript* t);

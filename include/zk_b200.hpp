@@ -160,6 +160,76 @@ class ProductPoly {
     std::vector<MultiLinearPolynomial<F>> polys_;
 };
 
+// P(x) = sum_t prod_{k in terms[t]} polynomials[k](x)  (beyond the reference's ProductPoly): the GKR
+// layer polynomial add.Wb + add.Wc + mul.Wb.Wc is polynomials = {add, mul, Wb, Wc}, terms = {{0,2},{0,3},{1,2,3}}.
+// Same surface as ProductPoly; a single term listing every table once is the reference's ProductPoly.
+template <class F>
+class SumOfProductsPoly {
+   public:
+    SumOfProductsPoly(std::vector<MultiLinearPolynomial<F>> polynomials, std::vector<std::vector<uint8_t>> terms)
+        : polys_(std::move(polynomials)), terms_(std::move(terms)) {
+        auto h = handles();
+        check(zk_product_check(h.empty() ? nullptr : (const zk_table* const*)h.data(), (unsigned)h.size()));
+        if (terms_.empty()) throw Error(ZK_ERR_EMPTY_PRODUCT);
+        for (auto& t : terms_) {
+            if (t.empty()) throw Error(ZK_ERR_EMPTY_PRODUCT);
+            for (uint8_t k : t)
+                if (k >= polys_.size()) throw Error(ZK_ERR_INVALID_ARG);
+            len_.push_back((uint8_t)t.size());
+            fac_.insert(fac_.end(), t.begin(), t.end());
+        }
+    }
+    size_t n_vars() const { return polys_[0].n_vars(); }
+    F sum() const {  // the honest claim
+        F r;
+        auto h = handles();
+        check(zk_sop_sum(Context::instance().get(), (const zk_table* const*)h.data(), (unsigned)h.size(), len_.data(), fac_.data(),
+                         (unsigned)len_.size(), r.limbs.data()));
+        return r;
+    }
+    F evaluate(const std::vector<F>& a) const {
+        F r;
+        auto h = handles();
+        check(zk_sop_evaluate(Context::instance().get(), (const zk_table* const*)h.data(), (unsigned)h.size(), len_.data(), fac_.data(),
+                              (unsigned)len_.size(), a.empty() ? nullptr : a[0].limbs.data(), (unsigned)a.size(), r.limbs.data()));
+        return r;
+    }
+    std::vector<F> round_poly(unsigned degree) const {  // prover.rs:48-56 for the sum of products
+        std::vector<F> out(degree + 1);
+        auto h = handles();
+        check(zk_sop_round_poly(Context::instance().get(), (const zk_table* const*)h.data(), (unsigned)h.size(), len_.data(), fac_.data(),
+                                (unsigned)len_.size(), degree, out[0].limbs.data()));
+        return out;
+    }
+    SumOfProductsPoly partial_evaluate(size_t initial_var, const std::vector<F>& a) const {
+        std::vector<MultiLinearPolynomial<F>> out;
+        for (auto& p : polys_) out.push_back(p.partial_evaluate(initial_var, a));
+        return SumOfProductsPoly(std::move(out), terms_);
+    }
+    std::vector<uint8_t> to_bytes() const {
+        std::vector<uint8_t> b;
+        for (auto& p : polys_) { auto x = p.to_bytes(); b.insert(b.end(), x.begin(), x.end()); }
+        return b;
+    }
+    SumOfProductsPoly clone() const {
+        std::vector<MultiLinearPolynomial<F>> out;
+        for (auto& p : polys_) out.push_back(p.clone());
+        return SumOfProductsPoly(std::move(out), terms_);
+    }
+    std::vector<zk_table*> handles() const {
+        std::vector<zk_table*> h;
+        for (auto& p : polys_) h.push_back(p.handle());
+        return h;
+    }
+    const std::vector<uint8_t>& term_len() const { return len_; }
+    const std::vector<uint8_t>& term_factors() const { return fac_; }
+
+   private:
+    std::vector<MultiLinearPolynomial<F>> polys_;
+    std::vector<std::vector<uint8_t>> terms_;
+    std::vector<uint8_t> len_, fac_;
+};
+
 template <class F>
 struct SumcheckProof {  // sumcheck/src/lib.rs:8-11
     F sum;
@@ -179,7 +249,25 @@ struct SumcheckProver {  // sumcheck/src/prover.rs:9-74
         return run(std::move(poly), sum, false);
     }
 
+    // the same loop over a sum of products (zk_sumcheck_prove_sop)
+    static SumcheckProof<F> prove(SumOfProductsPoly<F> poly, const F& sum) { return run_sop(std::move(poly), sum, true).first; }
+    static std::pair<SumcheckProof<F>, std::vector<F>> prove_partial(SumOfProductsPoly<F> poly, const F& sum) {
+        return run_sop(std::move(poly), sum, false);
+    }
+
    private:
+    static std::pair<SumcheckProof<F>, std::vector<F>> run_sop(SumOfProductsPoly<F> poly, const F& sum, bool absorb) {
+        const size_t n = poly.n_vars(), np = (size_t)MAX_VAR_DEGREE + 1;
+        std::vector<F> rp(n * np + 1), ch(n + 1);
+        auto h = poly.handles();
+        check(zk_sumcheck_prove_sop(Context::instance().get(), h.data(), (unsigned)h.size(), poly.term_len().data(),
+                                    poly.term_factors().data(), (unsigned)poly.term_len().size(), MAX_VAR_DEGREE, sum.limbs.data(),
+                                    absorb ? 1 : 0, rp[0].limbs.data(), ch[0].limbs.data(), nullptr));
+        SumcheckProof<F> proof{sum, {}};
+        for (size_t i = 0; i < n; i++) proof.round_polys.emplace_back(rp.begin() + i * np, rp.begin() + (i + 1) * np);
+        ch.resize(n);
+        return {proof, ch};
+    }
     static std::pair<SumcheckProof<F>, std::vector<F>> run(ProductPoly<F> poly, const F& sum, bool absorb) {
         const size_t n = poly.n_vars(), np = (size_t)MAX_VAR_DEGREE + 1;
         std::vector<F> rp(n * np + 1), ch(n + 1);

@@ -377,6 +377,79 @@ EXPORT int zko_prove_fast(int field, uint64_t *const *tables, unsigned m, unsign
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Sum of products  P(x) = sum_t prod_{k in term t} A_k(x)   (NOT in the reference,
+ * whose ProductPoly is one product, product_poly.rs:4-10).  The loop is prover.rs:33-73 verbatim
+ * with "prod_reduce().iter().sum()" read as the hypercube sum of P: append the sum, per round the
+ * evaluations at t = 0..degree (fold of every table at t, evaluation_form.rs:68), a challenge, the
+ * fold at it.  term_fac is n_terms rows of 8 table indices, term_len[t] of them used.
+ * Written REFERENCE-SHAPED on purpose (a partial_evaluate clone per table and point, a materialised
+ * table of P, a separate sum pass) so that it shares no structure with the GPU kernel it checks.
+ * ---------------------------------------------------------------------------------------- */
+static fe sop_table_sum(fe *const *tabs, size_t len, const uint8_t *term_len, const uint8_t *term_fac, unsigned n_terms,
+                        const field_t *F) {
+    fe *P = (fe *)malloc(len * sizeof(fe));
+    for (size_t j = 0; j < len; j++) P[j] = f_zero();
+    fe *prod = (fe *)malloc(len * sizeof(fe));
+    for (unsigned t = 0; t < n_terms; t++) {
+        memcpy(prod, tabs[term_fac[8 * t]], len * sizeof(fe));
+        for (unsigned i = 1; i < term_len[t]; i++) {
+            const fe *B = tabs[term_fac[8 * t + i]];
+            for (size_t j = 0; j < len; j++) prod[j] = f_mul(&prod[j], &B[j], F);
+        }
+        for (size_t j = 0; j < len; j++) P[j] = f_add(&P[j], &prod[j], F);
+    }
+    fe acc = f_zero();
+    for (size_t j = 0; j < len; j++) acc = f_add(&acc, &P[j], F);
+    free(prod); free(P);
+    return acc;
+}
+EXPORT int zko_sop_sum(int field, const uint64_t *const *tables, unsigned n_tables, unsigned n_vars,
+                       const uint8_t *term_len, const uint8_t *term_fac, unsigned n_terms, uint64_t out[4]) {
+    const field_t *F = &FIELDS[field]; (void)n_tables;
+    fe s = sop_table_sum((fe *const *)tables, (size_t)1 << n_vars, term_len, term_fac, n_terms, F);
+    memcpy(out, s.v, 32);
+    return 0;
+}
+EXPORT int zko_prove_sop(int field, const uint64_t *const *tables, unsigned n_tables, unsigned n_vars,
+                         const uint8_t *term_len, const uint8_t *term_fac, unsigned n_terms, unsigned degree,
+                         const uint64_t sum[4], int absorb, uint64_t *round_polys_out, uint64_t *challenges_out,
+                         uint64_t *finals_out) {
+    const field_t *F = &FIELDS[field];
+    keccak_t tr; k_init(&tr);
+    size_t n = (size_t)1 << n_vars;
+    fe **poly = (fe **)malloc(n_tables * sizeof(fe *));
+    for (unsigned k = 0; k < n_tables; k++) { poly[k] = (fe *)malloc(n * sizeof(fe)); memcpy(poly[k], tables[k], n * sizeof(fe)); }
+    uint8_t be[32];
+    if (absorb) {
+        for (unsigned k = 0; k < n_tables; k++) for (size_t j = 0; j < n; j++) { f_to_be32(&poly[k][j], be, F); k_update(&tr, be, 32); }
+    }
+    fe s; memcpy(s.v, sum, 32); f_to_be32(&s, be, F); k_update(&tr, be, 32);
+    unsigned nv = n_vars;
+    for (unsigned round = 0; round < n_vars; round++) {
+        size_t half = (size_t)1 << (nv - 1);
+        for (unsigned t = 0; t <= degree; t++) {
+            fe ft = f_from_u64(t, F);
+            fe **pe = (fe **)malloc(n_tables * sizeof(fe *));
+            for (unsigned k = 0; k < n_tables; k++) pe[k] = mle_partial_evaluate(poly[k], nv, 0, &ft, 1, F);
+            fe acc = sop_table_sum(pe, half, term_len, term_fac, n_terms, F);
+            memcpy(round_polys_out + 4 * ((size_t)round * (degree + 1) + t), acc.v, 32);
+            f_to_be32(&acc, be, F); k_update(&tr, be, 32);
+            for (unsigned k = 0; k < n_tables; k++) free(pe[k]);
+            free(pe);
+        }
+        fe r = t_sample(&tr, F);
+        memcpy(challenges_out + 4 * (size_t)round, r.v, 32);
+        for (unsigned k = 0; k < n_tables; k++) {
+            fe *nx = mle_partial_evaluate(poly[k], nv, 0, &r, 1, F); free(poly[k]); poly[k] = nx;
+        }
+        nv--;
+    }
+    for (unsigned k = 0; k < n_tables; k++) { if (finals_out) memcpy(finals_out + 4 * k, poly[k][0].v, 32); free(poly[k]); }
+    free(poly);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * SumcheckVerifier::verify_internal — sumcheck/src/verifier.rs:44-78, with
  * UnivariatePolynomial::interpolate (univariate_poly.rs:43-80, Lagrange over x = 0..D in
  * coefficient form) and Horner evaluate (:29-40).

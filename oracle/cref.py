@@ -33,6 +33,8 @@ def lib():
         _lib = C.CDLL(_SO)
         _lib.zko_prove.restype = C.c_int
         _lib.zko_prove_fast.restype = C.c_int
+        _lib.zko_prove_sop.restype = C.c_int
+        _lib.zko_sop_sum.restype = C.c_int
         _lib.zko_verify_internal.restype = C.c_int
         _lib.zko_fft.restype = C.c_int
         _lib.zko_fft_fast.restype = C.c_int
@@ -126,6 +128,36 @@ def prove(field: int, tables, n_vars: int, degree: int, sum_mont: np.ndarray, ab
     else:
         rc = lib().zko_prove(field, _ptr_array(tables), m, n_vars, degree, _p(sum_mont), int(bool(absorb)), _p(rp), _p(ch),
                              _p(fin))
+    assert rc == 0
+    return rp, ch, fin
+
+
+def _terms_flat(terms):
+    """terms: list of lists of table indices -> (term_len u8[n_terms], term_fac u8[n_terms*8], packed u8[sum len])."""
+    tl = np.array([len(t) for t in terms], dtype=np.uint8)
+    tf = np.zeros((len(terms), 8), dtype=np.uint8)
+    for i, t in enumerate(terms):
+        tf[i, : len(t)] = t
+    return tl, np.ascontiguousarray(tf.reshape(-1))
+
+
+def sop_sum(field: int, tables, terms, n_vars: int) -> np.ndarray:
+    tl, tf = _terms_flat(terms)
+    out = np.empty(4, dtype=np.uint64)
+    lib().zko_sop_sum(field, _ptr_array(tables), len(tables), n_vars, tl.ctypes.data_as(u8p), tf.ctypes.data_as(u8p),
+                      len(terms), _p(out))
+    return out
+
+
+def prove_sop(field: int, tables, terms, n_vars: int, degree: int, sum_mont: np.ndarray, absorb: bool = False):
+    """Sum-of-products prover.  Returns (round_polys (n,degree+1,4), challenges (n,4), finals (n_tables,4))."""
+    tl, tf = _terms_flat(terms)
+    rp = np.zeros((n_vars, degree + 1, 4), dtype=np.uint64)
+    ch = np.zeros((n_vars, 4), dtype=np.uint64)
+    fin = np.zeros((len(tables), 4), dtype=np.uint64)
+    sum_mont = np.ascontiguousarray(sum_mont, dtype=np.uint64)
+    rc = lib().zko_prove_sop(field, _ptr_array(tables), len(tables), n_vars, tl.ctypes.data_as(u8p), tf.ctypes.data_as(u8p),
+                             len(terms), degree, _p(sum_mont), int(bool(absorb)), _p(rp), _p(ch), _p(fin))
     assert rc == 0
     return rp, ch, fin
 

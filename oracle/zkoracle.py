@@ -313,6 +313,73 @@ class ProductPoly:
         return ProductPoly([MultiLinearPolynomial(q.F, q.n_vars(), list(q.evaluations)) for q in self.polynomials])
 
 
+class SumOfProductsPoly:
+    """P(x) = sum_t prod_{k in terms[t]} polynomials[k](x)   (SURVEY.md 8f-4).
+
+    NOT in the reference: its ProductPoly is a single product (product_poly.rs:4-10) and the GKR crate readme.md:9
+    links is absent.  This class is the smallest extension that lets the reference's own prover loop
+    (SumcheckProver.prove_internal, prover.rs:33-73) run unchanged over a GKR layer polynomial
+    add.Wb + add.Wc + mul.Wb.Wc: it offers the same four methods the loop calls on a ProductPoly — n_vars,
+    partial_evaluate, prod_reduce (here: the table of P, sum of the terms' element-wise products) and to_bytes
+    (the tables in order).  With a single term listing every table once it IS ProductPoly (tests pin that)."""
+
+    def __init__(self, polynomials, terms):
+        if len(polynomials) == 0 or len(terms) == 0 or any(len(t) == 0 for t in terms):
+            raise OracleError("cannot create product polynomial from empty polynomials")
+        expected = polynomials[0].n_vars()
+        if not all(q.n_vars() == expected for q in polynomials):
+            raise OracleError(
+                "cannot create product polynomial from polynomial that don't share the same number of variables"
+            )
+        if any(k < 0 or k >= len(polynomials) for t in terms for k in t):
+            raise OracleError("invalid argument")
+        self._n_vars = expected
+        self.polynomials = list(polynomials)
+        self.terms = [list(t) for t in terms]
+        self.F = polynomials[0].F
+
+    def n_vars(self) -> int:
+        return self._n_vars
+
+    def partial_evaluate(self, initial_var: int, assignments):
+        return SumOfProductsPoly([q.partial_evaluate(initial_var, assignments) for q in self.polynomials], self.terms)
+
+    def prod_reduce(self):
+        p = self.F.p
+        result = [0] * (1 << self._n_vars)
+        for term in self.terms:
+            prod = list(self.polynomials[term[0]].evaluation_slice())
+            for k in term[1:]:
+                for i, e in enumerate(self.polynomials[k].evaluation_slice()):
+                    prod[i] = (prod[i] * e) % p
+            for i, e in enumerate(prod):
+                result[i] = (result[i] + e) % p
+        return result
+
+    def evaluate(self, assignments) -> int:
+        if len(assignments) != self._n_vars:
+            raise OracleError("evaluate must assign to all variables")
+        vals = [q.evaluate(assignments) for q in self.polynomials]
+        return self.combine(vals)
+
+    def combine(self, table_values) -> int:
+        total = 0
+        for term in self.terms:
+            prod = 1
+            for k in term:
+                prod = (prod * table_values[k]) % self.F.p
+            total = (total + prod) % self.F.p
+        return total
+
+    def to_bytes(self) -> bytes:
+        return b"".join(q.to_bytes() for q in self.polynomials)
+
+    def clone(self):
+        return SumOfProductsPoly(
+            [MultiLinearPolynomial(q.F, q.n_vars(), list(q.evaluations)) for q in self.polynomials], self.terms
+        )
+
+
 # --------------------------------------------------------------------------------------
 # polynomial::univariate_poly  (verifier side only; polynomial/src/univariate_poly.rs)
 # --------------------------------------------------------------------------------------

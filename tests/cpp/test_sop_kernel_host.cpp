@@ -1,0 +1,187 @@
+// Host replay of the sum-of-products round kernel (zk_b200/csrc/sop_kernel.cuh), CPU suite.
+//
+// The kernel source is compiled here as plain C++: the CUDA decorations expand to nothing outside nvcc, the device
+// field arithmetic (inline PTX in field.cuh, compiled out without __CUDACC__) is replaced by host_field.hpp's
+// word-serial Montgomery arithmetic, shared memory is an ordinary array, and the grid is replayed block by block,
+// thread by thread.  What this pins without a GPU: the pair / quadruple index conventions of the fused in-place
+// fold (evaluation_form.rs:40-80 with initial_var = 0), the term bookkeeping, the evaluation points t = 0..D, the
+// grid-stride loop with ragged sizes.  What it cannot pin (the PTX multiplier, the block/grid reduction) is shared
+// with the product kernels and covered by the GPU suite.
+// The expected values come from an independent, deliberately naive model written below: fold out of place, then
+// evaluate every term at every t from scratch with multiplications by t.
+#include <cuda_runtime.h>  // vector types only (plain g++)
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#define __launch_bounds__(...)
+static uint3 threadIdx, blockIdx;
+static dim3 gridDim, blockDim;
+
+#include "kernels.h"
+#include "host_field.hpp"
+
+namespace zk {
+namespace {
+
+constexpr int kThreads = 128;
+const host::Field* g_field = nullptr;
+host::El g_challenge;                       // the launch-wide fold multiplier (the device reads it from FixedMul)
+std::vector<host::El> g_sums;               // what reduce_publish would publish
+alignas(32) uint4 sop_smem[2 * 2 * kMaxFactors * kThreads];
+
+inline host::El el(const Fe& a) { host::El e; std::memcpy(e.v, a.v, 32); return e; }
+inline Fe fe(const host::El& e) { Fe a; std::memcpy(a.v, e.v, 32); return a; }
+template <class F> Fe fe_zero() { return fe(g_field->zero()); }
+template <class F> Fe fe_add(const Fe& a, const Fe& b) { return fe(g_field->add(el(a), el(b))); }
+template <class F> Fe fe_sub(const Fe& a, const Fe& b) { return fe(g_field->sub(el(a), el(b))); }
+template <class F> Fe fe_mul(const Fe& a, const Fe& b) { return fe(g_field->mul(el(a), el(b))); }
+template <class F> Fe fe_fold_fixed(const Fe& l, const Fe& h, const FixedMul&) {  // l - r (l - h)
+    return fe(g_field->sub(el(l), g_field->mul(g_challenge, g_field->sub(el(l), el(h)))));
+}
+inline Fe ld_fe_stream(const Fe* p) { return *p; }
+inline void st_fe(Fe* p, const Fe& v) { *p = v; }
+struct ReduceArgs {};
+template <class F, int NP>
+void reduce_publish(const Fe* acc, const ReduceArgs&) {
+    for (int t = 0; t < NP; t++) g_sums[(size_t)t] = g_field->add(g_sums[(size_t)t], el(acc[t]));
+}
+
+}  // namespace
+}  // namespace zk
+
+#include "sop_kernel.cuh"
+
+using zk::Fe;
+using zk::host::El;
+using zk::host::Field;
+
+static uint64_t rng_state = 0x9E3779B97F4A7C15ULL;
+static uint64_t rnd() {
+    uint64_t z = (rng_state += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+static El rnd_el(const Field& F) {  // a product of two random words times a third: spread over the whole field
+    El a = F.from_u64(rnd()), b = F.from_u64(rnd()), c = F.from_u64(rnd());
+    return F.add(F.mul(F.mul(a, b), F.mul(c, b)), a);
+}
+
+template <class FT, int D, bool FOLD>
+static void replay(const zk::TablePtrs& tabs, const zk::SopSpec& spec, uint64_t q, unsigned grid) {
+    gridDim = dim3(grid, 1, 1);
+    blockDim = dim3(zk::kThreads, 1, 1);
+    for (unsigned b = 0; b < grid; b++)
+        for (unsigned t = 0; t < (unsigned)zk::kThreads; t++) {
+            blockIdx = uint3{b, 0, 0};
+            threadIdx = uint3{t, 0, 0};
+            zk::sop_round_kernel<FT, D, FOLD>(tabs, spec, q, zk::FixedMul{}, zk::ReduceArgs{});
+        }
+}
+
+template <class FT, int D>
+static long run_case(int field, unsigned log_len, bool fold, const zk::SopSpec& spec, unsigned grid) {
+    const Field F(field);
+    zk::g_field = &F;
+    const size_t len = (size_t)1 << log_len;  // table length entering the launch
+    std::vector<std::vector<El>> T((size_t)spec.n_tables, std::vector<El>(len));
+    for (auto& t : T)
+        for (auto& e : t) e = rnd_el(F);
+    // edge values in the first table: 0, 1, p-1
+    T[0][0] = F.zero();
+    T[0][len - 1] = F.one();
+    if (len > 2) T[0][1] = F.sub(F.zero(), F.one());
+    const El r = rnd_el(F);
+    zk::g_challenge = r;
+
+    // naive model
+    std::vector<std::vector<El>> M = T;
+    size_t cur = len;
+    if (fold) {
+        cur = len / 2;
+        for (auto& t : M) {
+            std::vector<El> nx(cur);
+            for (size_t j = 0; j < cur; j++) nx[j] = F.sub(t[j], F.mul(r, F.sub(t[j], t[j + cur])));  // pair (j, j + N/2)
+            t = nx;
+        }
+    }
+    const size_t half = cur / 2;
+    std::vector<El> want((size_t)D + 1, F.zero());
+    for (int t = 0; t <= D; t++) {
+        const El ft = F.from_u64((uint64_t)t);
+        for (size_t j = 0; j < half; j++)
+            for (int term = 0; term < spec.n_terms; term++) {
+                El pr = F.one();
+                for (int i = 0; i < (int)spec.len[term]; i++) {
+                    const std::vector<El>& A = M[spec.fac[term][i]];
+                    pr = F.mul(pr, F.sub(A[j], F.mul(ft, F.sub(A[j], A[j + half]))));  // left - t (left - right)
+                }
+                want[(size_t)t] = F.add(want[(size_t)t], pr);
+            }
+    }
+
+    // the kernel source, replayed
+    std::vector<std::vector<Fe>> dev((size_t)spec.n_tables, std::vector<Fe>(len));
+    zk::TablePtrs tabs{};
+    for (int k = 0; k < spec.n_tables; k++) {
+        for (size_t j = 0; j < len; j++) dev[(size_t)k][j] = zk::fe(T[(size_t)k][j]);
+        tabs.t[k] = dev[(size_t)k].data();
+    }
+    zk::g_sums.assign((size_t)D + 1, F.zero());
+    if (fold) replay<FT, D, true>(tabs, spec, len / 4, grid);
+    else replay<FT, D, false>(tabs, spec, len / 2, grid);
+
+    long bad = 0;
+    for (int t = 0; t <= D; t++) bad += (zk::g_sums[(size_t)t] != want[(size_t)t]);
+    if (fold)  // the folded tables are the first half of the buffers, in place
+        for (int k = 0; k < spec.n_tables; k++)
+            for (size_t j = 0; j < cur; j++) bad += (zk::el(dev[(size_t)k][j]) != M[(size_t)k][j]);
+    return bad;
+}
+
+static zk::SopSpec make_spec(int n_tables, std::vector<std::vector<int>> terms) {
+    zk::SopSpec s{};
+    s.n_tables = n_tables;
+    s.n_terms = (int)terms.size();
+    for (size_t t = 0; t < terms.size(); t++) {
+        s.len[t] = (uint8_t)terms[t].size();
+        for (size_t i = 0; i < terms[t].size(); i++) s.fac[t][i] = (uint8_t)terms[t][i];
+    }
+    return s;
+}
+
+int main() {
+    long bad = 0, cases = 0;
+    const zk::SopSpec gkr = make_spec(4, {{0, 2}, {0, 3}, {1, 2, 3}});
+    const zk::SopSpec sq = make_spec(2, {{0, 0}, {1}});
+    const zk::SopSpec wide = make_spec(8, {{0, 1}, {2, 3}, {4, 5}, {6, 7}, {0, 7}, {1, 6}, {2, 5}, {3, 4}});
+    const zk::SopSpec one = make_spec(3, {{0, 1, 2}});
+    for (int field = 0; field < 2; field++) {
+        for (unsigned log_len = 1; log_len <= 11; log_len++) {
+            for (int fold = 0; fold < 2; fold++) {
+                if (fold && log_len < 2) continue;  // the fused launch needs 4 entries
+                for (unsigned grid : {1u, 3u}) {
+                    if (field == 0) {
+                        bad += run_case<zk::Fr381, 3>(field, log_len, fold, gkr, grid);
+                        bad += run_case<zk::Fr381, 2>(field, log_len, fold, sq, grid);
+                        bad += run_case<zk::Fr381, 2>(field, log_len, fold, wide, grid);
+                        bad += run_case<zk::Fr381, 4>(field, log_len, fold, one, grid);
+                        bad += run_case<zk::Fr381, 1>(field, log_len, fold, gkr, grid);
+                    } else {
+                        bad += run_case<zk::Fr377, 3>(field, log_len, fold, gkr, grid);
+                        bad += run_case<zk::Fr377, 2>(field, log_len, fold, sq, grid);
+                        bad += run_case<zk::Fr377, 2>(field, log_len, fold, wide, grid);
+                        bad += run_case<zk::Fr377, 4>(field, log_len, fold, one, grid);
+                        bad += run_case<zk::Fr377, 1>(field, log_len, fold, gkr, grid);
+                    }
+                    cases += 5;
+                }
+            }
+        }
+    }
+    std::printf("%ld cases, %ld mismatches\n", cases, bad);
+    return bad ? 1 : 0;
+}

@@ -300,6 +300,83 @@ class ProductPoly:
         return len(self.polynomials) == len(other.polynomials) and all(a == b for a, b in zip(self.polynomials, other.polynomials))
 
 
+# ---- sum of products (beyond the reference's ProductPoly) ------------------------------------
+class SumOfProductsPoly:
+    """P(x) = sum_t prod_{k in terms[t]} polynomials[k](x) — e.g. the GKR layer polynomial add.Wb + add.Wc + mul.Wb.Wc
+    with polynomials = [add, mul, Wb, Wc] and terms = [[0, 2], [0, 3], [1, 2, 3]].  Same surface as ProductPoly
+    (the four methods the prover loop of sumcheck/src/prover.rs:33-73 calls, plus evaluate for the verifier's final
+    check); a single term listing every table once is the reference's ProductPoly."""
+
+    def __init__(self, polynomials: Sequence[MultiLinearPolynomial], terms: Sequence[Sequence[int]]):
+        self.polynomials = list(polynomials)
+        self.terms = [list(t) for t in terms]
+        self.ctx = self.polynomials[0].ctx if self.polynomials else Context.default()
+        self._term_len = np.array([len(t) for t in self.terms], dtype=np.uint8)
+        self._term_fac = np.array([k for t in self.terms for k in t] or [0], dtype=np.uint8)
+
+    @classmethod
+    def new(cls, polynomials: Sequence[MultiLinearPolynomial], terms: Sequence[Sequence[int]]) -> "SumOfProductsPoly":
+        polys = list(polynomials)
+        _check(lib().zk_product_check(_table_array(polys), len(polys)))
+        if len(terms) == 0 or any(len(t) == 0 for t in terms):
+            raise ZkError(3, lib().zk_status_string(3).decode())
+        if len(terms) > 8 or any(len(t) > 8 for t in terms):
+            raise ZkError(13, lib().zk_status_string(13).decode())
+        if any(not (0 <= int(k) < len(polys)) for t in terms for k in t):
+            raise ZkError(12, lib().zk_status_string(12).decode())
+        return cls(polys, terms)
+
+    def _arr(self):
+        return _table_array(self.polynomials)
+
+    def _terms(self):
+        return self._term_len.ctypes.data, self._term_fac.ctypes.data, len(self.terms)
+
+    def n_vars(self) -> int:
+        return self.polynomials[0].n_vars()
+
+    @property
+    def field(self) -> int:
+        return self.polynomials[0].field
+
+    def partial_evaluate(self, initial_var: int, assignments: Sequence[int]) -> "SumOfProductsPoly":
+        return SumOfProductsPoly([q.partial_evaluate(initial_var, assignments) for q in self.polynomials], self.terms)
+
+    def evaluate(self, assignments: Sequence[int]) -> int:
+        a = to_mont(self.field, list(assignments)) if len(assignments) else np.zeros((0, 4), dtype=np.uint64)
+        out = np.zeros(4, dtype=np.uint64)
+        self.ctx.check(lib().zk_sop_evaluate(self.ctx.h, self._arr(), len(self.polynomials), *self._terms(),
+                                             a.ctypes.data if a.size else None, a.shape[0], out.ctypes.data))
+        return from_mont(self.field, out)[0]
+
+    def combine(self, table_values: Sequence[int]) -> int:
+        """P at a point from the tables' values there (host only)."""
+        v = to_mont(self.field, list(table_values))
+        out = np.zeros(4, dtype=np.uint64)
+        _check(lib().zk_sop_combine(self.field, *self._terms(), v.ctypes.data, v.shape[0], out.ctypes.data))
+        return from_mont(self.field, out)[0]
+
+    def sum_mont(self) -> np.ndarray:
+        out = np.zeros(4, dtype=np.uint64)
+        self.ctx.check(lib().zk_sop_sum(self.ctx.h, self._arr(), len(self.polynomials), *self._terms(), out.ctypes.data))
+        return out
+
+    def sum(self) -> int:
+        return from_mont(self.field, self.sum_mont())[0]
+
+    def round_poly(self, degree: int) -> List[int]:
+        out = np.zeros((degree + 1, 4), dtype=np.uint64)
+        self.ctx.check(lib().zk_sop_round_poly(self.ctx.h, self._arr(), len(self.polynomials), *self._terms(), degree,
+                                               out.ctypes.data))
+        return from_mont(self.field, out)
+
+    def to_bytes(self) -> bytes:
+        return b"".join(q.to_bytes() for q in self.polynomials)
+
+    def clone(self) -> "SumOfProductsPoly":
+        return SumOfProductsPoly([q.clone() for q in self.polynomials], self.terms)
+
+
 # ---- sumcheck ---------------------------------------------------------------------------------------------
 class SumcheckProof:
     """sumcheck/src/lib.rs:8-11."""
@@ -355,8 +432,13 @@ class SumcheckProver:
         rp = np.zeros((n, d1, 4), dtype=np.uint64)
         ch = np.zeros((n, 4), dtype=np.uint64)
         fin = np.zeros((m, 4), dtype=np.uint64)
-        poly.ctx.check(lib().zk_sumcheck_prove(poly.ctx.h, poly._arr(), m, self.max_var_degree, sm.ctypes.data, int(absorb),
-                                               rp.ctypes.data, ch.ctypes.data, fin.ctypes.data))
+        if isinstance(poly, SumOfProductsPoly):
+            poly.ctx.check(lib().zk_sumcheck_prove_sop(poly.ctx.h, poly._arr(), m, *poly._terms(), self.max_var_degree,
+                                                       sm.ctypes.data, int(absorb), rp.ctypes.data, ch.ctypes.data,
+                                                       fin.ctypes.data))
+        else:
+            poly.ctx.check(lib().zk_sumcheck_prove(poly.ctx.h, poly._arr(), m, self.max_var_degree, sm.ctypes.data, int(absorb),
+                                                   rp.ctypes.data, ch.ctypes.data, fin.ctypes.data))
         vals = from_mont(field, rp.reshape(-1, 4)) if n else []
         rps = [vals[i * d1 : (i + 1) * d1] for i in range(n)]
         proof = SumcheckProof(field, sum_ % MODULUS[field], rps, rp, sm)

@@ -70,6 +70,11 @@ SIGNATURES = {
     "zk_sumcheck_verify": (C.c_int, [vp, vpp, C.c_uint, vp, vp, C.c_uint, C.c_uint]),
     "zk_sumcheck_verify_partial": (C.c_int, [C.c_int, vp, vp, C.c_uint, C.c_uint, vp, vp]),
     "zk_sumcheck_proof_dump": (C.c_int, [C.c_int, vp, vp, C.c_uint, C.c_uint, vp, vp, C.c_uint, vp, C.c_size_t, C.POINTER(C.c_size_t), vp]),
+    "zk_sop_round_poly": (C.c_int, [vp, vpp, C.c_uint, vp, vp, C.c_uint, C.c_uint, vp]),
+    "zk_sop_sum": (C.c_int, [vp, vpp, C.c_uint, vp, vp, C.c_uint, vp]),
+    "zk_sop_evaluate": (C.c_int, [vp, vpp, C.c_uint, vp, vp, C.c_uint, vp, C.c_uint, vp]),
+    "zk_sop_combine": (C.c_int, [C.c_int, vp, vp, C.c_uint, vp, C.c_uint, vp]),
+    "zk_sumcheck_prove_sop": (C.c_int, [vp, vpp, C.c_uint, vp, vp, C.c_uint, C.c_uint, vp, C.c_int, vp, vp, vp]),
     "zk_transcript_new": (vp, []),
     "zk_transcript_free": (None, [vp]),
     "zk_transcript_append": (None, [vp, C.c_char_p, C.c_size_t]),

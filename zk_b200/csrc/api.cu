@@ -784,9 +784,12 @@ struct ProveTimer {
 
 }  // namespace
 
-int zk_sumcheck_prove(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned degree, const uint64_t sum[4],
+// The round loop of prover.rs:33-73.  `sop` == nullptr: the reference's ProductPoly (the m tables are the factors);
+// otherwise the polynomial is the sum of products `*sop` over the m tables — same transcript
+// protocol, same folds, only the round-sum kernels differ.
+static int prove_core(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned degree, const uint64_t sum[4],
                       int absorb_initial_poly, uint64_t* round_polys_out, uint64_t* challenges_out,
-                      uint64_t* final_evals_out) {
+                      uint64_t* final_evals_out, const zk::SopSpec* sop) {
     if (!ctx || !sum) return fail(ctx, ZK_ERR_INVALID_ARG);
     int st = product_check(ctx, tables, m, true);
     if (st != ZK_OK) return st;
@@ -843,6 +846,16 @@ int zk_sumcheck_prove(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
         return ZK_OK;
     };
 
+    // round sums of the current tables / fold at r fused with the next round's sums
+    auto launch_sums = [&]() -> cudaError_t {
+        return sop ? zk::launch_sop_round_poly(field, cur, *sop, (int)degree, cur_len / 2, ctx->scratch, ctx->stream, &ctx->launches)
+                   : zk::launch_round_poly(field, cur, (int)m, (int)degree, cur_len / 2, ctx->scratch, ctx->stream, &ctx->launches);
+    };
+    auto launch_fold_sums = [&](const Fe& rf, const Fe* claim_ptr) -> cudaError_t {
+        return sop ? zk::launch_sop_fold_round_poly(field, cur, *sop, (int)degree, cur_len, rf, ctx->scratch, ctx->stream, &ctx->launches)
+                   : zk::launch_fold_round_poly(field, cur, (int)m, (int)degree, cur_len, rf, ctx->scratch, ctx->stream, &ctx->launches, claim_ptr);
+    };
+
     std::vector<uint64_t> S((size_t)np * 4);
     const RoundPolyEvaluator round_eval(F, np);
     size_t ev = 0;
@@ -859,7 +872,7 @@ int zk_sumcheck_prove(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
             st = gather();
             if (st != ZK_OK) { cleanup(); return st; }
         }
-        cudaError_t e = timed([&] { next_seq(ctx, sharded); return zk::launch_round_poly(field, cur, (int)m, (int)degree, cur_len / 2, ctx->scratch, ctx->stream, &ctx->launches); });
+        cudaError_t e = timed([&] { next_seq(ctx, sharded); return launch_sums(); });
         if (e != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "round_poly"); }
         if (perf_log_enabled()) {
             cudaStreamSynchronize(ctx->stream);
@@ -895,21 +908,21 @@ int zk_sumcheck_prove(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
             if (e != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "fold"); }
             st = gather();
             if (st != ZK_OK) { cleanup(); return st; }
-            e = timed([&] { next_seq(ctx, sharded); return zk::launch_round_poly(field, cur, (int)m, (int)degree, cur_len / 2, ctx->scratch, ctx->stream, &ctx->launches); });
+            e = timed([&] { next_seq(ctx, sharded); return launch_sums(); });
         } else {
             // S_{round+1}(0) + S_{round+1}(1) = S_round(r): the kernel skips the t = 1 term and derives it (sharded:
             // the map is linear, so the value goes to rank 0 and zero to the others before the all-reduce).
             // Only when the D+1 evaluations determine the round polynomial, i.e. D >= m: the reference does not
             // validate MAX_VAR_DEGREE against the factor count (prover.rs:48-56), and with D < m the interpolant
             // through S(0..D) is not the true polynomial, so there the t = 1 term is computed like the others.
-            const bool derive_s1 = degree >= 1 && degree >= m;
+            const bool derive_s1 = !sop && degree >= 1 && degree >= m;
             Fe claim_next = Fe{};
             if (derive_s1 && (!sharded || ctx->rank == 0)) {
                 const El c = round_eval.at(S.data(), r);
                 std::memcpy(claim_next.v, c.v, 32);
             }
             const Fe* claim_ptr = derive_s1 ? &claim_next : nullptr;
-            e = timed([&] { next_seq(ctx, sharded); return zk::launch_fold_round_poly(field, cur, (int)m, (int)degree, cur_len, rf, ctx->scratch, ctx->stream, &ctx->launches, claim_ptr); });
+            e = timed([&] { next_seq(ctx, sharded); return launch_fold_sums(rf, claim_ptr); });
             cur_len /= 2;
         }
         if (e != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "fold_round_poly"); }
@@ -942,6 +955,13 @@ int zk_sumcheck_prove(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
     count(ctx);
     ctx->prove_ms[0] = timer.ms();
     return ZK_OK;
+}
+
+int zk_sumcheck_prove(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned degree, const uint64_t sum[4],
+                      int absorb_initial_poly, uint64_t* round_polys_out, uint64_t* challenges_out,
+                      uint64_t* final_evals_out) {
+    return prove_core(ctx, tables, m, degree, sum, absorb_initial_poly, round_polys_out, challenges_out, final_evals_out,
+                      nullptr);
 }
 
 int zk_sumcheck_prove_host(zk_ctx* ctx, int field, const uint64_t* const* host_tables, unsigned m, unsigned n_vars,
@@ -1016,6 +1036,132 @@ int zk_sumcheck_prove_host(zk_ctx* ctx, int field, const uint64_t* const* host_t
                                final_evals_out);
     free_all();
     return st;
+}
+
+// ---- sum of products (beyond the reference's ProductPoly) --------------------------------
+namespace {
+
+// Validates (tables, terms) and builds the kernels' SopSpec.  term_len[t] factors of term t follow each other in
+// term_factors; every factor is an index into tables[].
+int sop_spec_from(zk_ctx* ctx, const zk_table* const* tables, unsigned n_tables, const uint8_t* term_len,
+                  const uint8_t* term_factors, unsigned n_terms, zk::SopSpec* spec) {
+    int st = product_check(ctx, tables, n_tables, true);
+    if (st != ZK_OK) return st;
+    for (unsigned a = 0; a < n_tables; a++)
+        for (unsigned b = a + 1; b < n_tables; b++)
+            if (tables[a] == tables[b] || tables[a]->data == tables[b]->data)
+                return fail(ctx, ZK_ERR_INVALID_ARG, "a table is listed twice: list it once and repeat its index in the terms");
+    if (n_terms == 0 || !term_len || !term_factors) return fail(ctx, ZK_ERR_EMPTY_PRODUCT);
+    if (n_terms > (unsigned)zk::kMaxTerms) return fail(ctx, ZK_ERR_UNSUPPORTED, "more than 8 terms");
+    *spec = zk::SopSpec{};
+    spec->n_tables = (int)n_tables;
+    spec->n_terms = (int)n_terms;
+    size_t off = 0;
+    for (unsigned t = 0; t < n_terms; t++) {
+        if (term_len[t] == 0) return fail(ctx, ZK_ERR_EMPTY_PRODUCT);
+        if (term_len[t] > ZK_MAX_FACTORS) return fail(ctx, ZK_ERR_UNSUPPORTED, "more than ZK_MAX_FACTORS factors in a term");
+        spec->len[t] = term_len[t];
+        for (unsigned i = 0; i < term_len[t]; i++) {
+            if (term_factors[off + i] >= n_tables) return fail(ctx, ZK_ERR_INVALID_ARG, "term factor index out of range");
+            spec->fac[t][i] = term_factors[off + i];
+        }
+        off += term_len[t];
+    }
+    return ZK_OK;
+}
+
+}  // namespace
+
+int zk_sop_combine(int field, const uint8_t* term_len, const uint8_t* term_factors, unsigned n_terms,
+                   const uint64_t* table_values, unsigned n_tables, uint64_t out[4]) {
+    if (!valid_field(field) || !term_len || !term_factors || !table_values || !out || n_terms == 0) return ZK_ERR_INVALID_ARG;
+    const Field F(field);
+    El acc = F.zero();
+    size_t off = 0;
+    for (unsigned t = 0; t < n_terms; t++) {
+        if (term_len[t] == 0) return ZK_ERR_INVALID_ARG;
+        El pr = F.one();
+        for (unsigned i = 0; i < term_len[t]; i++) {
+            if (term_factors[off + i] >= n_tables) return ZK_ERR_INVALID_ARG;
+            pr = F.mul(pr, el_from(table_values + 4 * (size_t)term_factors[off + i]));
+        }
+        acc = F.add(acc, pr);
+        off += term_len[t];
+    }
+    std::memcpy(out, acc.v, 32);
+    return ZK_OK;
+}
+
+int zk_sop_round_poly(zk_ctx* ctx, const zk_table* const* tables, unsigned n_tables, const uint8_t* term_len,
+                      const uint8_t* term_factors, unsigned n_terms, unsigned degree, uint64_t* out) {
+    if (!ctx || !out) return fail(ctx, ZK_ERR_INVALID_ARG);
+    zk::SopSpec spec;
+    int st = sop_spec_from(ctx, tables, n_tables, term_len, term_factors, n_terms, &spec);
+    if (st != ZK_OK) return st;
+    if (!zk::sop_degree_supported((int)degree)) return fail(ctx, ZK_ERR_UNSUPPORTED, "sum-of-products rounds support MAX_VAR_DEGREE 1..4");
+    if (tables[0]->n_vars == 0 || tables[0]->local_len < 2) return fail(ctx, ZK_ERR_VAR_RANGE);
+    CU(ctx, cudaSetDevice(ctx->device));
+    next_seq(ctx, true);
+    CU(ctx, zk::launch_sop_round_poly(tables[0]->field, ptrs_of(tables, n_tables), spec, (int)degree, tables[0]->local_len / 2,
+                                      ctx->scratch, ctx->stream, &ctx->launches));
+    st = finish_reduction(ctx, tables[0]->field, (int)degree + 1, out, true);
+    count(ctx);
+    return st;
+}
+
+int zk_sop_sum(zk_ctx* ctx, const zk_table* const* tables, unsigned n_tables, const uint8_t* term_len,
+               const uint8_t* term_factors, unsigned n_terms, uint64_t out[4]) {
+    if (!ctx || !out) return fail(ctx, ZK_ERR_INVALID_ARG);
+    int st = product_check(ctx, tables, n_tables, true);
+    if (st != ZK_OK) return st;
+    if (tables[0]->n_vars == 0) {  // a constant: the sum over the empty hypercube is the value itself
+        if (ctx->world > 1) return fail(ctx, ZK_ERR_UNSUPPORTED, "zero-variable tables on a sharded context");
+        zk::SopSpec spec;
+        st = sop_spec_from(ctx, tables, n_tables, term_len, term_factors, n_terms, &spec);
+        if (st != ZK_OK) return st;
+        CU(ctx, cudaSetDevice(ctx->device));
+        std::vector<uint64_t> vals((size_t)n_tables * 4);
+        for (unsigned k = 0; k < n_tables; k++)
+            CU(ctx, cudaMemcpyAsync(vals.data() + 4 * (size_t)k, tables[k]->data, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        return zk_sop_combine(tables[0]->field, term_len, term_factors, n_terms, vals.data(), n_tables, out);
+    }
+    // S(0) + S(1) of the first round polynomial is the sum over the whole hypercube
+    uint64_t s01[8];
+    st = zk_sop_round_poly(ctx, tables, n_tables, term_len, term_factors, n_terms, 1, s01);
+    if (st != ZK_OK) return st;
+    const Field F(tables[0]->field);
+    const El sum = F.add(el_from(s01), el_from(s01 + 4));
+    std::memcpy(out, sum.v, 32);
+    return ZK_OK;
+}
+
+int zk_sop_evaluate(zk_ctx* ctx, const zk_table* const* tables, unsigned n_tables, const uint8_t* term_len,
+                    const uint8_t* term_factors, unsigned n_terms, const uint64_t* point, unsigned len, uint64_t out[4]) {
+    if (!ctx || !out) return fail(ctx, ZK_ERR_INVALID_ARG);
+    zk::SopSpec spec;
+    int st = sop_spec_from(ctx, tables, n_tables, term_len, term_factors, n_terms, &spec);
+    if (st != ZK_OK) return st;
+    if (len != tables[0]->n_vars) return fail(ctx, ZK_ERR_EVALUATE_ARITY);
+    std::vector<uint64_t> vals((size_t)n_tables * 4);
+    for (unsigned k = 0; k < n_tables; k++) {
+        st = zk_mle_evaluate(ctx, tables[k], point, len, vals.data() + 4 * (size_t)k);
+        if (st != ZK_OK) return st;
+    }
+    return zk_sop_combine(tables[0]->field, term_len, term_factors, n_terms, vals.data(), n_tables, out);
+}
+
+int zk_sumcheck_prove_sop(zk_ctx* ctx, zk_table* const* tables, unsigned n_tables, const uint8_t* term_len,
+                          const uint8_t* term_factors, unsigned n_terms, unsigned degree, const uint64_t sum[4],
+                          int absorb_initial_poly, uint64_t* round_polys_out, uint64_t* challenges_out,
+                          uint64_t* final_evals_out) {
+    if (!ctx || !sum) return fail(ctx, ZK_ERR_INVALID_ARG);
+    zk::SopSpec spec;
+    int st = sop_spec_from(ctx, tables, n_tables, term_len, term_factors, n_terms, &spec);
+    if (st != ZK_OK) return st;
+    if (!zk::sop_degree_supported((int)degree)) return fail(ctx, ZK_ERR_UNSUPPORTED, "sum-of-products rounds support MAX_VAR_DEGREE 1..4");
+    return prove_core(ctx, tables, n_tables, degree, sum, absorb_initial_poly, round_polys_out, challenges_out,
+                      final_evals_out, &spec);
 }
 
 // ---- verifier -------------------------------------------------------------------------------------

@@ -55,6 +55,26 @@ cudaError_t launch_product_sum(int field, const TablePtrs& tabs, int m, uint64_t
 // true if (m, degree) has a fully fused template instantiation
 bool has_fused_path(int m, int degree);
 
+// ---- sum of products (kernels_sop.cu) -------------------------------------------------------------
+// P(x) = sum_t prod_{k in term t} A_k(x): the shape of a GKR layer polynomial add.(Wb + Wc) + mul.Wb.Wc, which the
+// reference's ProductPoly (polynomial/src/product_poly.rs:4-10, a pure product) cannot express.
+// A table may appear in several terms (and several times in one term); it is read — and folded — once per item.
+constexpr int kMaxTerms = 8;
+struct SopSpec {
+    int n_tables;                          // distinct tables, <= kMaxFactors
+    int n_terms;                           // <= kMaxTerms
+    uint8_t len[kMaxTerms];                // factors of term t, 1..kMaxFactors
+    uint8_t fac[kMaxTerms][kMaxFactors];   // table indices of term t
+};
+bool sop_degree_supported(int degree);  // 1..4, like the fused product path
+// S(t) = sum_{j<half} sum_terms prod_k [A_k[j] + t (A_k[j+half] - A_k[j])], t = 0..degree  -> scratch.result_*
+cudaError_t launch_sop_round_poly(int field, const TablePtrs& tabs, const SopSpec& spec, int degree, uint64_t half,
+                                  const ReduceScratch& scratch, cudaStream_t stream, int* launches);
+// fold every table of the n_prev-entry set at r in place (n_prev >= 4), and the next round's S(t) in the same pass
+cudaError_t launch_sop_fold_round_poly(int field, const TablePtrs& tabs, const SopSpec& spec, int degree,
+                                       uint64_t n_prev, const Fe& r, const ReduceScratch& scratch, cudaStream_t stream,
+                                       int* launches);
+
 // ---- MLE utilities (kernels_mle.cu) --------------------------------------------------------------
 // General partial_evaluate step for variable `initial_var` of an nv-variable table: out[k] = fold of the
 // pair (insert_bit(k,pos,0), |1<<pos), pos = nv-1-initial_var; out-of-place (evaluation_form.rs:54-72).

@@ -1,0 +1,89 @@
+// kernels_sop.cu — sumcheck rounds over a SUM of products of MLE tables on sm_100a.
+//
+//   P(x) = sum_t prod_{k in term t} A_k(x)        e.g. the GKR layer polynomial add.Wb + add.Wc + mul.Wb.Wc
+//
+// The reference has no such type: its ProductPoly is one product (polynomial/src/product_poly.rs:4-10) and readme.md:9
+// only points at a GKR crate that is not in the tree.  The protocol is the reference's own (sumcheck/src/prover.rs:33-73):
+// per round the evaluations S(t), t = 0..D, of the sum over the remaining hypercube with variable 0 bound to t, then
+// every table is folded at the challenge (evaluation_form.rs:40-80, pair (j, j + N/2), l - r (l - h)).  A single-term
+// sum is exactly the reference's ProductPoly proof (tests pin that), and S is linear in the terms.
+//
+// One pass per round, like the product kernels: round 0 reads every table once; every later round folds the
+// quadruple (j, j+q, j+2q, j+3q) of every table at the previous challenge, writes the two folded values back in
+// place and forms the next round's sums from them — a table shared by several terms is read and folded once.
+// The per-item values e_k(t) = lo_k + t (hi_k - lo_k) of all tables live in shared memory (2 x n_tables elements per
+// thread) because the terms index them with run-time table numbers; the products run on the general fe_mul.
+// First version of this row: no deferred reduction, FP64 folds or dynamic chunks yet (kernels_sumcheck.cu has those).
+#include "kernels.h"
+#include "reduce.cuh"
+#include "sop_kernel.cuh"
+
+namespace zk {
+namespace {
+
+constexpr size_t sop_smem_bytes(int n_tables) { return (size_t)2 * n_tables * kThreads * sizeof(Fe); }
+
+template <class F, int D, bool FOLD>
+cudaError_t do_sop(const TablePtrs& tabs, const SopSpec& spec, uint64_t q, const Fe& r, const ReduceScratch& s,
+                   cudaStream_t st) {
+    static const cudaError_t attr = cudaFuncSetAttribute(sop_round_kernel<F, D, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)sop_smem_bytes(kMaxFactors));
+    if (attr != cudaSuccess) return attr;
+    const size_t smem = sop_smem_bytes(spec.n_tables);
+    static int bpsm_cache[kMaxFactors + 1] = {0};
+    int& bpsm = bpsm_cache[spec.n_tables];
+    if (bpsm == 0) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sop_round_kernel<F, D, FOLD>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
+        bpsm = nb;
+    }
+    const unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
+    const FixedMul tab = FOLD ? make_fixed<F>(r) : FixedMul{};
+    sop_round_kernel<F, D, FOLD><<<grid, kThreads, smem, st>>>(tabs, spec, q, tab, make_ra(s, 0));
+    return cudaGetLastError();
+}
+
+template <class F, bool FOLD>
+cudaError_t do_sop_deg(const TablePtrs& tabs, const SopSpec& spec, int degree, uint64_t q, const Fe& r,
+                       const ReduceScratch& s, cudaStream_t st) {
+    switch (degree) {
+        case 1: return do_sop<F, 1, FOLD>(tabs, spec, q, r, s, st);
+        case 2: return do_sop<F, 2, FOLD>(tabs, spec, q, r, s, st);
+        case 3: return do_sop<F, 3, FOLD>(tabs, spec, q, r, s, st);
+        case 4: return do_sop<F, 4, FOLD>(tabs, spec, q, r, s, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+bool spec_ok(const SopSpec& spec) {
+    if (spec.n_tables < 1 || spec.n_tables > kMaxFactors || spec.n_terms < 1 || spec.n_terms > kMaxTerms) return false;
+    for (int t = 0; t < spec.n_terms; t++) {
+        if (spec.len[t] < 1 || spec.len[t] > kMaxFactors) return false;
+        for (int i = 0; i < (int)spec.len[t]; i++)
+            if ((int)spec.fac[t][i] >= spec.n_tables) return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+bool sop_degree_supported(int degree) { return degree >= 1 && degree <= 4; }
+
+cudaError_t launch_sop_round_poly(int field, const TablePtrs& tabs, const SopSpec& spec, int degree, uint64_t half,
+                                  const ReduceScratch& scratch, cudaStream_t stream, int* launches) {
+    if (!spec_ok(spec) || half < 1) return cudaErrorInvalidValue;
+    ++*launches;
+    return field == Fr381::ID ? do_sop_deg<Fr381, false>(tabs, spec, degree, half, Fe{}, scratch, stream)
+                              : do_sop_deg<Fr377, false>(tabs, spec, degree, half, Fe{}, scratch, stream);
+}
+
+cudaError_t launch_sop_fold_round_poly(int field, const TablePtrs& tabs, const SopSpec& spec, int degree,
+                                       uint64_t n_prev, const Fe& r, const ReduceScratch& scratch, cudaStream_t stream,
+                                       int* launches) {
+    if (!spec_ok(spec) || n_prev < 4) return cudaErrorInvalidValue;
+    ++*launches;
+    return field == Fr381::ID ? do_sop_deg<Fr381, true>(tabs, spec, degree, n_prev / 4, r, scratch, stream)
+                              : do_sop_deg<Fr377, true>(tabs, spec, degree, n_prev / 4, r, scratch, stream);
+}
+
+}  // namespace zk

@@ -1,0 +1,65 @@
+// sop_kernel.cuh — the sum-of-products round kernel (see kernels_sop.cu for what it computes and why).
+// Kept in its own header so that tests/cpp/test_sop_kernel_host.cpp can replay the very same source on the host,
+// thread by thread, with host_field.hpp standing in for the device arithmetic: the index conventions (pairs, the
+// in-place quadruple fold, term bookkeeping) are then checked on the CPU, without a GPU.
+// Needs in scope: Fe / FixedMul / TablePtrs / SopSpec (kernels.h), the fe_* and ld/st functions (field.cuh on the
+// device), kThreads, ReduceArgs and reduce_publish (reduce.cuh on the device).
+#pragma once
+
+namespace zk {
+namespace {
+
+template <class F, int D, bool FOLD>
+__global__ void __launch_bounds__(kThreads)
+    sop_round_kernel(TablePtrs tabs, const __grid_constant__ SopSpec spec, uint64_t q,
+                     const __grid_constant__ FixedMul rtab, ReduceArgs ra) {
+    extern __shared__ __align__(32) uint4 sop_smem[];  // Fe [2 * n_tables][kThreads]: e_k then d_k
+    Fe* const ev = reinterpret_cast<Fe*>(sop_smem) + threadIdx.x;
+    const int nt = spec.n_tables;
+    Fe* const dv = ev + (size_t)nt * kThreads;
+    Fe acc[D + 1];
+#pragma unroll
+    for (int t = 0; t <= D; t++) acc[t] = fe_zero<F>();
+    const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+#pragma unroll 1
+    for (uint64_t j = (uint64_t)blockIdx.x * kThreads + threadIdx.x; j < q; j += stride) {
+#pragma unroll 1
+        for (int k = 0; k < nt; k++) {
+            Fe* T = tabs.t[k];
+            Fe lo, hi;
+            if (FOLD) {  // T has 4q entries: fold (j, j+2q) and (j+q, j+3q) at r, write back to j and j+q
+                const Fe x0 = ld_fe_stream(T + j), x2 = ld_fe_stream(T + j + 2 * q);
+                const Fe x1 = ld_fe_stream(T + j + q), x3 = ld_fe_stream(T + j + 3 * q);
+                lo = fe_fold_fixed<F>(x0, x2, rtab);
+                hi = fe_fold_fixed<F>(x1, x3, rtab);
+                st_fe(T + j, lo);
+                st_fe(T + j + q, hi);
+            } else {  // T has 2q entries: the pair is (j, j+q)
+                lo = ld_fe_stream(T + j);
+                hi = ld_fe_stream(T + j + q);
+            }
+            ev[(size_t)k * kThreads] = lo;
+            dv[(size_t)k * kThreads] = fe_sub<F>(hi, lo);
+        }
+#pragma unroll
+        for (int t = 0; t <= D; t++) {
+            Fe s = fe_zero<F>();
+#pragma unroll 1
+            for (int term = 0; term < spec.n_terms; term++) {
+                Fe p = ev[(size_t)spec.fac[term][0] * kThreads];
+#pragma unroll 1
+                for (int i = 1; i < (int)spec.len[term]; i++) p = fe_mul<F>(p, ev[(size_t)spec.fac[term][i] * kThreads]);
+                s = fe_add<F>(s, p);
+            }
+            acc[t] = fe_add<F>(acc[t], s);
+            if (t < D) {  // e_k(t+1) = e_k(t) + (hi_k - lo_k)
+#pragma unroll 1
+                for (int k = 0; k < nt; k++) ev[(size_t)k * kThreads] = fe_add<F>(ev[(size_t)k * kThreads], dv[(size_t)k * kThreads]);
+            }
+        }
+    }
+    reduce_publish<F, D + 1>(acc, ra);
+}
+
+}  // namespace
+}  // namespace zk
