@@ -3,7 +3,7 @@
 2^n-entry tables, MAX_VAR_DEGREE 3, prove_partial with the tables resident; the (3,3) ProductPoly proof at the same
 size beside it.  Times come from the library itself (zk_ctx_last_prove_ms: host clock around the round loop, CUDA
 events around every launch) — no torch import.  One JSON line per polynomial.
-usage: python scripts/bench_sop.py [log_n=24] [reps=3]"""
+usage: python scripts/bench_sop.py [log_n=24] [reps=3] [sop]     ("sop": skip the product proof)"""
 import json
 import os
 import statistics
@@ -23,8 +23,10 @@ def main():
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     ctx = zk.Context(0)
     d = 3
-    for name, nt, make in (("sum_of_products_gkr", 4, lambda t: zk.SumOfProductsPoly.new(t, GKR)),
-                           ("product_3", 3, lambda t: zk.ProductPoly.new(t))):
+    polys = [("sum_of_products_gkr", 4, lambda t: zk.SumOfProductsPoly.new(t, GKR)), ("product_3", 3, lambda t: zk.ProductPoly.new(t))]
+    if len(sys.argv) > 3 and sys.argv[3] == "sop":
+        polys = polys[:1]
+    for name, nt, make in polys:
         tabs = [zk.MultiLinearPolynomial.generate(n, 20 + k, ctx=ctx) for k in range(nt)]
         poly = make(tabs)
         claim = poly.sum()
@@ -46,7 +48,8 @@ def main():
         print(json.dumps({"poly": name, "log_n": n, "n_tables": nt, "degree": d, "prove_ms": tot, "kernel_ms": ker,
                           "first_round_ms": first, "alg_gbs": alg_bytes / (tot * 1e-3) / 1e9,
                           "first_fused_step_gbs": 48 * nt * (1 << n) / (first[1] * 1e-3) / 1e9 if len(first) > 1 else None,
-                          "verified_against_evaluate": bool(ok)}), flush=True)
+                          "verified_against_evaluate": bool(ok),
+                          "fold_pipe": os.environ.get("ZK_B200_SOP_FOLD_PIPE", "default")}), flush=True)
         del poly, tabs
 
 

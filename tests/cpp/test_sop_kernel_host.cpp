@@ -21,6 +21,7 @@ static uint3 threadIdx, blockIdx;
 static dim3 gridDim, blockDim;
 
 #include "kernels.h"
+#include "field_f64.cuh"
 #include "host_field.hpp"
 
 namespace zk {
@@ -43,9 +44,14 @@ template <class F> Fe fe_fold_fixed(const Fe& l, const Fe& h, const FixedMul&) {
 }
 inline Fe ld_fe_stream(const Fe* p) { return *p; }
 inline void st_fe(Fe* p, const Fe& v) { *p = v; }
-struct ReduceArgs {};
+template <class F> void fe_fold_fixed_f64_x2(Fe& lo, Fe& hi, const Fe& x0, const Fe& x1, const Fe& x2, const Fe& x3,
+                                             const FixedMulF64&) {  // the FP64-pipe variant computes the same two folds
+    lo = fe_fold_fixed<F>(x0, x2, FixedMul{});
+    hi = fe_fold_fixed<F>(x1, x3, FixedMul{});
+}
+struct ReduceArgs { int skip1; };
 template <class F, int NP>
-void reduce_publish(const Fe* acc, const ReduceArgs&) {
+void reduce_publish(const Fe* acc, const ReduceArgs&) {  // the harness applies S(1) = claim - S(0) after the last block
     for (int t = 0; t < NP; t++) g_sums[(size_t)t] = g_field->add(g_sums[(size_t)t], el(acc[t]));
 }
 
@@ -70,20 +76,20 @@ static El rnd_el(const Field& F) {  // a product of two random words times a thi
     return F.add(F.mul(F.mul(a, b), F.mul(c, b)), a);
 }
 
-template <class FT, int D, bool FOLD>
-static void replay(const zk::TablePtrs& tabs, const zk::SopSpec& spec, uint64_t q, unsigned grid) {
+template <class FT, int D, bool FOLD, bool F64>
+static void replay(const zk::TablePtrs& tabs, const zk::SopSpec& spec, uint64_t q, unsigned grid, int skip1) {
     gridDim = dim3(grid, 1, 1);
     blockDim = dim3(zk::kThreads, 1, 1);
     for (unsigned b = 0; b < grid; b++)
         for (unsigned t = 0; t < (unsigned)zk::kThreads; t++) {
             blockIdx = uint3{b, 0, 0};
             threadIdx = uint3{t, 0, 0};
-            zk::sop_round_kernel<FT, D, FOLD>(tabs, spec, q, zk::FixedMul{}, zk::ReduceArgs{});
+            zk::sop_round_kernel<FT, D, FOLD, F64>(tabs, spec, q, zk::FixedMul{}, zk::FixedMulF64Sel{}, zk::ReduceArgs{skip1});
         }
 }
 
 template <class FT, int D>
-static long run_case(int field, unsigned log_len, bool fold, const zk::SopSpec& spec, unsigned grid) {
+static long run_case(int field, unsigned log_len, bool fold, const zk::SopSpec& spec, unsigned grid, int mode) {
     const Field F(field);
     zk::g_field = &F;
     const size_t len = (size_t)1 << log_len;  // table length entering the launch
@@ -131,8 +137,15 @@ static long run_case(int field, unsigned log_len, bool fold, const zk::SopSpec& 
         tabs.t[k] = dev[(size_t)k].data();
     }
     zk::g_sums.assign((size_t)D + 1, F.zero());
-    if (fold) replay<FT, D, true>(tabs, spec, len / 4, grid);
-    else replay<FT, D, false>(tabs, spec, len / 2, grid);
+    // mode 0: every evaluation summed, integer folds; 1: S(1) derived from the claim; 2: S(1) derived, FP64 folds
+    if (fold && mode == 2) replay<FT, D, true, true>(tabs, spec, len / 4, grid, 1);
+    else if (fold) replay<FT, D, true, false>(tabs, spec, len / 4, grid, mode == 1);
+    else replay<FT, D, false, false>(tabs, spec, len / 2, grid, 1 /* ignored without a fold */);
+    if (fold && mode >= 1) {  // what the last block does with ra.claim = S(0) + S(1)
+        long untouched = (zk::g_sums[1] != F.zero());
+        zk::g_sums[1] = F.sub(F.add(want[0], want[1]), zk::g_sums[0]);
+        if (untouched) return 1000000;  // the t = 1 products were not skipped
+    }
 
     long bad = 0;
     for (int t = 0; t <= D; t++) bad += (zk::g_sums[(size_t)t] != want[(size_t)t]);
@@ -163,22 +176,23 @@ int main() {
         for (unsigned log_len = 1; log_len <= 11; log_len++) {
             for (int fold = 0; fold < 2; fold++) {
                 if (fold && log_len < 2) continue;  // the fused launch needs 4 entries
-                for (unsigned grid : {1u, 3u}) {
-                    if (field == 0) {
-                        bad += run_case<zk::Fr381, 3>(field, log_len, fold, gkr, grid);
-                        bad += run_case<zk::Fr381, 2>(field, log_len, fold, sq, grid);
-                        bad += run_case<zk::Fr381, 2>(field, log_len, fold, wide, grid);
-                        bad += run_case<zk::Fr381, 4>(field, log_len, fold, one, grid);
-                        bad += run_case<zk::Fr381, 1>(field, log_len, fold, gkr, grid);
-                    } else {
-                        bad += run_case<zk::Fr377, 3>(field, log_len, fold, gkr, grid);
-                        bad += run_case<zk::Fr377, 2>(field, log_len, fold, sq, grid);
-                        bad += run_case<zk::Fr377, 2>(field, log_len, fold, wide, grid);
-                        bad += run_case<zk::Fr377, 4>(field, log_len, fold, one, grid);
-                        bad += run_case<zk::Fr377, 1>(field, log_len, fold, gkr, grid);
+                for (unsigned grid : {1u, 3u})
+                    for (int mode = 0; mode < (fold ? 3 : 1); mode++) {
+                        if (field == 0) {
+                            bad += run_case<zk::Fr381, 3>(field, log_len, fold, gkr, grid, mode);
+                            bad += run_case<zk::Fr381, 2>(field, log_len, fold, sq, grid, mode);
+                            bad += run_case<zk::Fr381, 2>(field, log_len, fold, wide, grid, mode);
+                            bad += run_case<zk::Fr381, 4>(field, log_len, fold, one, grid, mode);
+                            bad += run_case<zk::Fr381, 1>(field, log_len, fold, sq, grid, mode);
+                        } else {
+                            bad += run_case<zk::Fr377, 3>(field, log_len, fold, gkr, grid, mode);
+                            bad += run_case<zk::Fr377, 2>(field, log_len, fold, sq, grid, mode);
+                            bad += run_case<zk::Fr377, 2>(field, log_len, fold, wide, grid, mode);
+                            bad += run_case<zk::Fr377, 4>(field, log_len, fold, one, grid, mode);
+                            bad += run_case<zk::Fr377, 1>(field, log_len, fold, sq, grid, mode);
+                        }
+                        cases += 5;
                     }
-                    cases += 5;
-                }
             }
         }
     }

@@ -73,6 +73,30 @@ def main():
             ok &= bool((srp == crp).all() and (sch == cch).all() and (sfin == cfin).all()); checks += 1
         if rank == 0 and not same:
             print(f"MISMATCH n={n} m={m} d={d} thr={thr}", flush=True)
+    # sum of products, GKR layer shape: sharded == single GPU == CPU oracle
+    GKR = [[0, 2], [0, 3], [1, 2, 3]]
+    for (n, d, thr) in [(16, 3, 4096), (16, 3, 1), (14, 2, 64), (6, 3, 4096), (20, 3, 4096)]:
+        if (1 << n) < world:
+            continue
+        sctx.set_gather_threshold(thr)
+        sp = zk.SumOfProductsPoly.new([zk.MultiLinearPolynomial.generate(n, 20 + k, seed=seed, ctx=sctx) for k in range(4)], GKR)
+        up = zk.SumOfProductsPoly.new([zk.MultiLinearPolynomial.generate(n, 20 + k, seed=seed, ctx=uctx) for k in range(4)], GKR)
+        sclaim, uclaim = sp.sum_mont(), up.sum_mont()
+        ok &= bool((sclaim == uclaim).all()); checks += 1
+        if (1 << n) // world >= 2:
+            ok &= sp.round_poly(d) == up.round_poly(d); checks += 1
+        claim_int = zk.from_mont(0, uclaim)[0]
+        sprover, uprover = zk.SumcheckProver(d), zk.SumcheckProver(d)
+        sproof, sch = sprover.prove_partial(sp, claim_int)
+        uproof, uch = uprover.prove_partial(up, claim_int)
+        same = bool((sproof._round_polys_mont == uproof._round_polys_mont).all()) and sch == uch and sprover.final_evals == uprover.final_evals
+        ok &= same; checks += 1
+        if n <= 16:
+            refs = [cref.gen_table(0, seed, 20 + k, n) for k in range(4)]
+            crp, cch, cfin = cref.prove_sop(0, refs, GKR, n, d, cref.sop_sum(0, refs, GKR, n))
+            ok &= bool((sproof._round_polys_mont == crp).all()) and sprover.final_evals == cref.mont_to_ints(0, cfin); checks += 1
+        if rank == 0 and not same:
+            print(f"SOP MISMATCH n={n} d={d} thr={thr}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

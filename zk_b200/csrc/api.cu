@@ -852,7 +852,7 @@ static int prove_core(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
                    : zk::launch_round_poly(field, cur, (int)m, (int)degree, cur_len / 2, ctx->scratch, ctx->stream, &ctx->launches);
     };
     auto launch_fold_sums = [&](const Fe& rf, const Fe* claim_ptr) -> cudaError_t {
-        return sop ? zk::launch_sop_fold_round_poly(field, cur, *sop, (int)degree, cur_len, rf, ctx->scratch, ctx->stream, &ctx->launches)
+        return sop ? zk::launch_sop_fold_round_poly(field, cur, *sop, (int)degree, cur_len, rf, ctx->scratch, ctx->stream, &ctx->launches, claim_ptr)
                    : zk::launch_fold_round_poly(field, cur, (int)m, (int)degree, cur_len, rf, ctx->scratch, ctx->stream, &ctx->launches, claim_ptr);
     };
 
@@ -915,7 +915,13 @@ static int prove_core(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
             // Only when the D+1 evaluations determine the round polynomial, i.e. D >= m: the reference does not
             // validate MAX_VAR_DEGREE against the factor count (prover.rs:48-56), and with D < m the interpolant
             // through S(0..D) is not the true polynomial, so there the t = 1 term is computed like the others.
-            const bool derive_s1 = !sop && degree >= 1 && degree >= m;
+            // (sum of products: D >= the longest term, the degree of the round polynomial)
+            unsigned true_degree = m;
+            if (sop) {
+                true_degree = 0;
+                for (int t = 0; t < sop->n_terms; t++) true_degree = sop->len[t] > true_degree ? sop->len[t] : true_degree;
+            }
+            const bool derive_s1 = degree >= 1 && degree >= true_degree;
             Fe claim_next = Fe{};
             if (derive_s1 && (!sharded || ctx->rank == 0)) {
                 const El c = round_eval.at(S.data(), r);

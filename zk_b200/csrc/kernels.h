@@ -70,10 +70,12 @@ bool sop_degree_supported(int degree);  // 1..4, like the fused product path
 // S(t) = sum_{j<half} sum_terms prod_k [A_k[j] + t (A_k[j+half] - A_k[j])], t = 0..degree  -> scratch.result_*
 cudaError_t launch_sop_round_poly(int field, const TablePtrs& tabs, const SopSpec& spec, int degree, uint64_t half,
                                   const ReduceScratch& scratch, cudaStream_t stream, int* launches);
-// fold every table of the n_prev-entry set at r in place (n_prev >= 4), and the next round's S(t) in the same pass
+// fold every table of the n_prev-entry set at r in place (n_prev >= 4), and the next round's S(t) in the same pass.
+// `claim` (optional): this rank's share of S_prev(r) = S(0) + S(1) of the round being computed; the kernel then skips
+// the t = 1 products and publishes S(1) = claim - S(0).  Only valid when degree >= the longest term.
 cudaError_t launch_sop_fold_round_poly(int field, const TablePtrs& tabs, const SopSpec& spec, int degree,
                                        uint64_t n_prev, const Fe& r, const ReduceScratch& scratch, cudaStream_t stream,
-                                       int* launches);
+                                       int* launches, const Fe* claim = nullptr);
 
 // ---- MLE utilities (kernels_mle.cu) --------------------------------------------------------------
 // General partial_evaluate step for variable `initial_var` of an nv-variable table: out[k] = fold of the

@@ -13,7 +13,11 @@
 // place and forms the next round's sums from them — a table shared by several terms is read and folded once.
 // The per-item values e_k(t) = lo_k + t (hi_k - lo_k) of all tables live in shared memory (2 x n_tables elements per
 // thread) because the terms index them with run-time table numbers; the products run on the general fe_mul.
-// First version of this row: no deferred reduction, FP64 folds or dynamic chunks yet (kernels_sumcheck.cu has those).
+// Rounds >= 1 derive S(1) from the previous round polynomial (one evaluation point less to multiply out) when
+// MAX_VAR_DEGREE covers the longest term; FP64 folds are wired behind ZK_B200_SOP_FOLD_PIPE.  No deferred
+// reduction or dynamic chunks yet (kernels_sumcheck.cu has those).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "reduce.cuh"
 #include "sop_kernel.cuh"
@@ -23,10 +27,10 @@ namespace {
 
 constexpr size_t sop_smem_bytes(int n_tables) { return (size_t)2 * n_tables * kThreads * sizeof(Fe); }
 
-template <class F, int D, bool FOLD>
-cudaError_t do_sop(const TablePtrs& tabs, const SopSpec& spec, uint64_t q, const Fe& r, const ReduceScratch& s,
-                   cudaStream_t st) {
-    static const cudaError_t attr = cudaFuncSetAttribute(sop_round_kernel<F, D, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <class F, int D, bool FOLD, bool F64>
+cudaError_t do_sop_v(const TablePtrs& tabs, const SopSpec& spec, uint64_t q, const Fe& r, const ReduceScratch& s,
+                     cudaStream_t st, const Fe* claim) {
+    static const cudaError_t attr = cudaFuncSetAttribute(sop_round_kernel<F, D, FOLD, F64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                          (int)sop_smem_bytes(kMaxFactors));
     if (attr != cudaSuccess) return attr;
     const size_t smem = sop_smem_bytes(spec.n_tables);
@@ -34,23 +38,45 @@ cudaError_t do_sop(const TablePtrs& tabs, const SopSpec& spec, uint64_t q, const
     int& bpsm = bpsm_cache[spec.n_tables];
     if (bpsm == 0) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sop_round_kernel<F, D, FOLD>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sop_round_kernel<F, D, FOLD, F64>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
         bpsm = nb;
     }
     const unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
-    const FixedMul tab = FOLD ? make_fixed<F>(r) : FixedMul{};
-    sop_round_kernel<F, D, FOLD><<<grid, kThreads, smem, st>>>(tabs, spec, q, tab, make_ra(s, 0));
+    const FixedMul tab = (FOLD && !F64) ? make_fixed<F>(r) : FixedMul{};
+    const FixedMulF64Sel tab64 = F64 ? make_fixed_f64<F>(r) : FixedMulF64Sel{};
+    ReduceArgs ra = make_ra(s, 0);
+    if (FOLD && claim) {
+        ra.skip1 = 1;
+        ra.claim = *claim;
+    }
+    sop_round_kernel<F, D, FOLD, F64><<<grid, kThreads, smem, st>>>(tabs, spec, q, tab, tab64, ra);
     return cudaGetLastError();
+}
+
+// Which pipe folds: ZK_B200_SOP_FOLD_PIPE=int|f64 (default int until the FP64 variant has been measured on this kernel)
+inline bool sop_fold_on_f64() {
+    static const bool on = [] {
+        const char* e = std::getenv("ZK_B200_SOP_FOLD_PIPE");
+        return e && e[0] == 'f';
+    }();
+    return on;
+}
+
+template <class F, int D, bool FOLD>
+cudaError_t do_sop(const TablePtrs& tabs, const SopSpec& spec, uint64_t q, const Fe& r, const ReduceScratch& s,
+                   cudaStream_t st, const Fe* claim) {
+    if (FOLD && sop_fold_on_f64()) return do_sop_v<F, D, FOLD, FOLD>(tabs, spec, q, r, s, st, claim);
+    return do_sop_v<F, D, FOLD, false>(tabs, spec, q, r, s, st, claim);
 }
 
 template <class F, bool FOLD>
 cudaError_t do_sop_deg(const TablePtrs& tabs, const SopSpec& spec, int degree, uint64_t q, const Fe& r,
-                       const ReduceScratch& s, cudaStream_t st) {
+                       const ReduceScratch& s, cudaStream_t st, const Fe* claim = nullptr) {
     switch (degree) {
-        case 1: return do_sop<F, 1, FOLD>(tabs, spec, q, r, s, st);
-        case 2: return do_sop<F, 2, FOLD>(tabs, spec, q, r, s, st);
-        case 3: return do_sop<F, 3, FOLD>(tabs, spec, q, r, s, st);
-        case 4: return do_sop<F, 4, FOLD>(tabs, spec, q, r, s, st);
+        case 1: return do_sop<F, 1, FOLD>(tabs, spec, q, r, s, st, claim);
+        case 2: return do_sop<F, 2, FOLD>(tabs, spec, q, r, s, st, claim);
+        case 3: return do_sop<F, 3, FOLD>(tabs, spec, q, r, s, st, claim);
+        case 4: return do_sop<F, 4, FOLD>(tabs, spec, q, r, s, st, claim);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -79,11 +105,11 @@ cudaError_t launch_sop_round_poly(int field, const TablePtrs& tabs, const SopSpe
 
 cudaError_t launch_sop_fold_round_poly(int field, const TablePtrs& tabs, const SopSpec& spec, int degree,
                                        uint64_t n_prev, const Fe& r, const ReduceScratch& scratch, cudaStream_t stream,
-                                       int* launches) {
+                                       int* launches, const Fe* claim) {
     if (!spec_ok(spec) || n_prev < 4) return cudaErrorInvalidValue;
     ++*launches;
-    return field == Fr381::ID ? do_sop_deg<Fr381, true>(tabs, spec, degree, n_prev / 4, r, scratch, stream)
-                              : do_sop_deg<Fr377, true>(tabs, spec, degree, n_prev / 4, r, scratch, stream);
+    return field == Fr381::ID ? do_sop_deg<Fr381, true>(tabs, spec, degree, n_prev / 4, r, scratch, stream, claim)
+                              : do_sop_deg<Fr377, true>(tabs, spec, degree, n_prev / 4, r, scratch, stream, claim);
 }
 
 }  // namespace zk

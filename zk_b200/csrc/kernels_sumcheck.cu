@@ -353,17 +353,6 @@ template <class F>
 Fe small_constant(unsigned t);  // Montgomery form of small integer t (host side)
 
 
-template <class F>
-FixedMulF64Sel make_fixed_f64(const Fe& r) {
-    host::Field HF(F::ID);
-    host::El rm;
-    std::memcpy(rm.v, r.v, 32);
-    FixedMulF64Sel t;
-    host::fixed_mul_table_f64(HF, rm, t.t[0].t);
-    t.t[1] = t.t[0];
-    return t;
-}
-
 // Which pipe folds: FP64 (field_f64.cuh) for items of two or more factors, where the product multiplications keep
 // the integer-multiply pipe busy (measured -3 % on the fused degree-3 step, -1.5 % at degree 2); the integer pipe
 // for a single table (HBM bound: the longer FP64 instruction stream only costs).  ZK_B200_FOLD_PIPE=int|f64 forces one.

@@ -6,6 +6,7 @@
 #pragma once
 #include <cstring>
 
+#include "field_f64.cuh"
 #include "host_field.hpp"
 #include "kernels.h"
 
@@ -208,6 +209,18 @@ Fe host_small_mont(unsigned t) {
     Fe r;
     for (int i = 0; i < 8; i++) r.v[i] = acc[i];
     return r;
+}
+
+// host: the FP64 multiples of the challenge for fe_fold_fixed_f64* (field_f64.cuh), both copies of the selector
+template <class F>
+FixedMulF64Sel make_fixed_f64(const Fe& r) {
+    host::Field HF(F::ID);
+    host::El rm;
+    std::memcpy(rm.v, r.v, 32);
+    FixedMulF64Sel t;
+    host::fixed_mul_table_f64(HF, rm, t.t[0].t);
+    t.t[1] = t.t[0];
+    return t;
 }
 
 }  // namespace
