@@ -191,3 +191,41 @@ def test_round_poly_evaluate_vs_oracle(zk, fid):
     one = zk.to_mont(fid, [1])
     assert lib.zk_round_poly_evaluate(fid, one.ctypes.data, 0, one.ctypes.data, out.ctypes.data) != 0
     assert lib.zk_round_poly_evaluate(fid, one.ctypes.data, 17, one.ctypes.data, out.ctypes.data) != 0
+
+
+def test_rust_ffi_is_in_sync_with_the_header():
+    """rust/zk-b200-sys/src/ffi.rs is generated from include/zk_b200.h (scripts/gen_rust_ffi.py): it must be the
+    generator's current output and declare every ZK_API entry point exactly once (no rustc here to tell us)."""
+    import re
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "gen_rust_ffi.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    header = open(os.path.join(ROOT, "include", "zk_b200.h")).read()
+    declared = re.findall(r"ZK_API[^;(]*?\b(zk_\w+)\s*\(", re.sub(r"/\*.*?\*/", " ", header, flags=re.S))
+    ffi = open(os.path.join(ROOT, "rust", "zk-b200-sys", "src", "ffi.rs")).read()
+    rust = re.findall(r"pub fn (zk_\w+)\(", ffi)
+    assert rust == declared and len(set(rust)) == len(rust) == 65
+
+
+def test_rust_sources_are_well_formed_and_only_call_declared_entry_points():
+    """Source-only Rust (rust/): brackets balance, and every `sys::zk_*` / `zk_*(` call names a declared entry point."""
+    import re
+
+    ffi = open(os.path.join(ROOT, "rust", "zk-b200-sys", "src", "ffi.rs")).read()
+    known = set(re.findall(r"pub fn (zk_\w+)\(", ffi)) | {"zk_ctx", "zk_table", "zk_transcript", "zk_microbench", "zk_b200_sys", "zk_b200"}
+    n_files = 0
+    for base, _, files in os.walk(os.path.join(ROOT, "rust")):
+        for f in files:
+            if not f.endswith(".rs"):
+                continue
+            n_files += 1
+            src = open(os.path.join(base, f)).read()
+            code = re.sub(r"//[^\n]*", "", src)
+            code = re.sub(r'"(?:\\.|[^"\\])*"', '""', code)
+            for a, b in ("()", "[]", "{}"):
+                assert code.count(a) == code.count(b), (f, a, code.count(a), code.count(b))
+            for name in re.findall(r"\b(zk_\w+)\b", code):
+                assert name in known, (f, name)
+    assert n_files >= 12
