@@ -17,6 +17,17 @@ pub struct SubClaim<F: PrimeField> {
     pub(crate) challenges: Vec<F>,
 }
 
+impl<F: PrimeField> SubClaim<F> {
+    // Accessors are an addition: the reference keeps both fields crate-private and offers none (lib.rs:17-20), so a
+    // caller outside the `sumcheck` crate cannot finish the check a sub-claim stands for.
+    pub fn sum(&self) -> F {
+        self.sum
+    }
+    pub fn challenges(&self) -> &[F] {
+        &self.challenges
+    }
+}
+
 impl<F: PrimeField> SumcheckProof<F> {
     /// Proof dump of SURVEY.md Appendix A.5 (the reference defines no serialiser): BE32(sum) || BE32 of every round
     /// evaluation; `zk_sumcheck_proof_dump` on the C side.
