@@ -107,6 +107,11 @@ ZK_API int zk_table_upload(zk_ctx* ctx, int field, const uint64_t* mont_aos, uin
 ZK_API int zk_table_generate(zk_ctx* ctx, int field, uint64_t seed, uint64_t table_id, unsigned n_vars, zk_table** out);
 /* Refill an existing table (e.g. one consumed by zk_sumcheck_prove) with synthetic table `table_id`: no allocation. */
 ZK_API int zk_table_regenerate(zk_ctx* ctx, zk_table* t, uint64_t seed, uint64_t table_id);
+/* Upload this rank's local entries as they are (local_len * world must equal 2^n_vars): a shard the caller already
+ * holds in the layout an entry point expects — the strided shard for the sumcheck entry points, the contiguous block
+ * for the inverse zk_ntt_sharded. */
+ZK_API int zk_table_upload_local(zk_ctx* ctx, int field, const uint64_t* local_mont_aos, uint64_t local_len, unsigned n_vars,
+                                 zk_table** out);
 ZK_API int zk_table_clone(zk_ctx* ctx, const zk_table* in, zk_table** out);
 ZK_API void zk_table_free(zk_table* t);
 ZK_API unsigned zk_table_n_vars(const zk_table* t);     /* n_vars() :30 */
@@ -226,6 +231,19 @@ ZK_API void zk_keccak256(const uint8_t* data, size_t len, uint8_t out[32]);
 ZK_API int zk_ntt(zk_ctx* ctx, zk_table* inout, int inverse);
 /* Host-buffer form: `len` must be a power of two (else ZK_ERR_NOT_POW2). */
 ZK_API int zk_ntt_host(zk_ctx* ctx, int field, uint64_t* mont_aos_inout, uint64_t len, int inverse);
+/* Multi-GPU fft / ifft on a sharded context (collective: every rank calls it).  Layout contract:
+ *   forward : `inout` holds this rank's STRIDED shard a[rank], a[rank + world], ... (what zk_table_upload /
+ *             zk_table_generate keep on a sharded context); on return it holds the CONTIGUOUS block
+ *             X[rank * N/world .. (rank+1) * N/world) of the natural-order transform;
+ *   inverse : contiguous block in (zk_table_upload_local), strided shard out — ifft(fft(a)) round-trips in place.
+ * world in {2, 4, 8}; N >= world^2 (else ZK_ERR_UNSUPPORTED); ZK_ERR_NO_ROOT as for zk_ntt.  Per rank: the
+ * single-GPU transform of its N/world entries, one twiddle multiplication per entry, two all-to-all exchanges (NCCL
+ * send/recv groups over NVLink) around a world-point DFT.  On an unsharded context it is zk_ntt. */
+ZK_API int zk_ntt_sharded(zk_ctx* ctx, zk_table* inout, int inverse);
+/* The same factorisation with `ranks` VIRTUAL ranks on one GPU (unsharded ctx, full table in and out, natural order,
+ * result identical to zk_ntt): every kernel and index map of the multi-GPU path with device-to-device copies in
+ * place of the NCCL exchanges — how the path is validated on a single GPU. */
+ZK_API int zk_ntt_virtual_sharded(zk_ctx* ctx, zk_table* inout, unsigned ranks, int inverse);
 
 /* ---- field helpers for harnesses (host; ark-ff conversions the reference calls) --------------------- */
 ZK_API int zk_field_from_canonical(int field, const uint64_t* canon, uint64_t* mont, size_t count); /* reduces mod p */

@@ -5,7 +5,8 @@
 
 Checks, for several (n, m, D) and gather thresholds: the sharded proof (strided sharding by the last-bound
 variables + NCCL all-reduce of the round polynomials + residual gather) is bit-identical to the single-GPU
-proof and to the CPU oracle; sharded upload/product_sum/round_poly agree too.  Prints one JSON line.
+proof and to the CPU oracle; sharded upload/product_sum/round_poly agree too; the same for the sum-of-products prover
+(GKR shape); the multi-GPU NTT (zk_ntt_sharded) against the oracle's fft, forward and round trip.  Prints one JSON line.
 """
 import json
 import os
@@ -97,6 +98,23 @@ def main():
             ok &= bool((sproof._round_polys_mont == crp).all()) and sprover.final_evals == cref.mont_to_ints(0, cfin); checks += 1
         if rank == 0 and not same:
             print(f"SOP MISMATCH n={n} d={d} thr={thr}", flush=True)
+    # multi-GPU NTT (zk_ntt_sharded): strided shard in -> contiguous block of the natural-order transform out, and back
+    g = world.bit_length() - 1
+    for fid in (0, 1):
+        for n in sorted({2 * g, 2 * g + 1, 12, 16, 20}):
+            if n < 2 * g or world not in (2, 4, 8):
+                continue
+            full = cref.gen_table(fid, seed, 3, n)
+            want = cref.fft(fid, full, n, fast=True)
+            M = (1 << n) // world
+            t = zk.MultiLinearPolynomial.new_local(n, full[rank::world], field=fid, ctx=sctx)
+            t.ntt_sharded()
+            fwd_ok = bool((t.evaluation_slice_mont() == want[rank * M:(rank + 1) * M]).all())
+            t.ntt_sharded(inverse=True)
+            back_ok = bool((t.evaluation_slice_mont() == full[rank::world]).all())
+            ok &= fwd_ok and back_ok; checks += 2
+            if not (fwd_ok and back_ok):
+                print(f"NTT MISMATCH rank={rank} field={fid} n={n} forward={fwd_ok} round_trip={back_ok}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -157,6 +157,28 @@ class MultiLinearPolynomial:
         return cls(h, ctx)
 
     @classmethod
+    def new_local(cls, n_vars: int, local_evaluations: np.ndarray, field: int = BLS12_381_FR, ctx: Optional[Context] = None):
+        """This rank's local entries uploaded as they are (zk_table_upload_local): (L,4) uint64 Montgomery limbs."""
+        ctx = ctx or Context.default()
+        mont = np.ascontiguousarray(local_evaluations, dtype=np.uint64).reshape(-1, 4)
+        h = C.c_void_p()
+        ctx.check(lib().zk_table_upload_local(ctx.h, field, mont.ctypes.data if mont.size else None, mont.shape[0], n_vars, C.byref(h)))
+        return cls(h, ctx)
+
+    def ntt_sharded(self, inverse: bool = False):
+        """Multi-GPU fft / ifft in place (zk_ntt_sharded): strided shard -> contiguous block (forward), the reverse
+        for the inverse.  Collective over the sharded context."""
+        self.ctx.check(lib().zk_ntt_sharded(self.ctx.h, self._h, int(inverse)))
+
+    def ntt_virtual_sharded(self, ranks: int, inverse: bool = False):
+        """The multi-GPU factorisation with `ranks` virtual ranks on this one GPU (zk_ntt_virtual_sharded)."""
+        self.ctx.check(lib().zk_ntt_virtual_sharded(self.ctx.h, self._h, ranks, int(inverse)))
+
+    def ntt(self, inverse: bool = False):
+        """fft / ifft of the table in place (zk_ntt), natural order in and out."""
+        self.ctx.check(lib().zk_ntt(self.ctx.h, self._h, int(inverse)))
+
+    @classmethod
     def generate(cls, n_vars: int, table_id: int, seed: int = DEFAULT_SEED, field: int = BLS12_381_FR,
                  ctx: Optional[Context] = None):
         """Deterministic synthetic table, generated on the device."""

@@ -49,6 +49,7 @@ SIGNATURES = {
     "zk_table_upload": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_uint, vpp]),
     "zk_table_generate": (C.c_int, [vp, C.c_int, C.c_uint64, C.c_uint64, C.c_uint, vpp]),
     "zk_table_regenerate": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64]),
+    "zk_table_upload_local": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_uint, vpp]),
     "zk_table_clone": (C.c_int, [vp, vp, vpp]),
     "zk_table_free": (None, [vp]),
     "zk_table_n_vars": (C.c_uint, [vp]),
@@ -83,6 +84,8 @@ SIGNATURES = {
     "zk_keccak256": (None, [C.c_char_p, C.c_size_t, vp]),
     "zk_ntt": (C.c_int, [vp, vp, C.c_int]),
     "zk_ntt_host": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_int]),
+    "zk_ntt_sharded": (C.c_int, [vp, vp, C.c_int]),
+    "zk_ntt_virtual_sharded": (C.c_int, [vp, vp, C.c_uint, C.c_int]),
     "zk_field_from_canonical": (C.c_int, [C.c_int, vp, vp, C.c_size_t]),
     "zk_field_to_canonical": (C.c_int, [C.c_int, vp, vp, C.c_size_t]),
     "zk_field_from_u64": (C.c_int, [C.c_int, C.c_uint64, vp]),

@@ -111,6 +111,21 @@ bool ntt_plan_is(const NttPlan*, int field, unsigned log_n, bool inverse);
 cudaError_t ntt_execute(NttPlan* plan, Fe* data, Fe** result, cudaStream_t stream, int* launches);
 void ntt_plan_adopt_scratch(NttPlan* plan, Fe* buf);
 
+// ---- multi-GPU NTT pieces (kernels_ntt_sharded.cu; the factorisation is described in ntt_sharded_kernels.cuh) ----
+// out[i] = base^(i << shift), i < count
+cudaError_t launch_pow_table(int field, Fe* out, uint64_t count, const Fe& base, unsigned shift, cudaStream_t stream,
+                             int* launches);
+// x[k] *= t_hi[k >> lo_bits] * t_lo[k & (2^lo_bits - 1)], k < m   (the inter-rank twiddles w_N^(q k))
+cudaError_t launch_twiddle_mul(int field, Fe* x, uint64_t m, const Fe* t_lo, const Fe* t_hi, unsigned lo_bits,
+                               cudaStream_t stream, int* launches);
+// out[c][j] = (scale *) sum_q w_G^(q c) in[q][j], j < chunk; ranks in {2, 4, 8}; w_half[i] = w_G^i, i < ranks/2
+// (the inverse root for the inverse transform); scale may be null
+cudaError_t launch_gdft(int field, int ranks, const Fe* in, Fe* out, uint64_t chunk, const Fe* w_half, const Fe* scale,
+                        cudaStream_t stream, int* launches);
+// out[q * L + j] = in[j * G + q]: strided shards of a full table, rank-major (inverse of launch_interleave)
+cudaError_t launch_deinterleave(const Fe* in, Fe* out, uint64_t local_len, unsigned world, cudaStream_t stream,
+                                int* launches);
+
 // ---- micro-benchmarks (microbench.cu) ------------------------------------------------------------
 struct MicrobenchResult {
     double imad_wide_per_s;     // independent IMAD.WIDE.U32 per second, whole chip
