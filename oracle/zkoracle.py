@@ -129,8 +129,10 @@ class Keccak256:
     (`update`, `finalize_reset`): transcript/src/lib.rs:2,17,22."""
 
     RATE = 136
+    DOMAIN = 0x01  # original Keccak padding; 0x06 would be SHA3-256 (same permutation, rate and capacity)
 
-    def __init__(self):
+    def __init__(self, domain: int = 0x01):
+        self.DOMAIN = domain
         self._reset()
 
     def _reset(self):
@@ -153,7 +155,7 @@ class Keccak256:
 
     def finalize_reset(self) -> bytes:
         pad = bytearray(self.buf) + bytearray(self.RATE - len(self.buf))
-        pad[len(self.buf)] ^= 0x01  # original Keccak domain/padding byte (SHA3 would be 0x06)
+        pad[len(self.buf)] ^= self.DOMAIN  # 0x01: original Keccak domain/padding byte (SHA3 would be 0x06)
         pad[self.RATE - 1] ^= 0x80
         self._absorb_block(bytes(pad))
         out = b"".join(self.state[i % 5][i // 5].to_bytes(8, "little") for i in range(4))

@@ -281,3 +281,47 @@ def test_fullsize_digest_file_is_the_oracles(cref):
     a = cref.prove(0, t2, 10, 3, cl, False, fast=True)
     b = cref.prove(0, t2, 10, 3, cl, False, fast=False)
     assert all((x == y).all() for x, y in zip(a, b))
+
+
+def test_keccak_sponge_pinned_by_hashlib_sha3_256():
+    """An implementation this repo did not write: Python's hashlib has no Keccak-256, but its SHA3-256 is the same
+    Keccak-f[1600], rate 136 and capacity 512 — only the domain byte of the padding differs (0x06 instead of 0x01).
+    Running the oracle's sponge with 0x06 must therefore reproduce hashlib.sha3_256 on every length around the block
+    boundaries and on multi-block messages in uneven chunks; the 0x01 byte itself is pinned by the published
+    Keccak-256 digests of "" and "abc" (test_keccak_kats)."""
+    import hashlib
+
+    msg = bytes((i * 131 + 7) & 0xFF for i in range(1000))
+    for n in list(range(0, 300)) + [407, 408, 409, 543, 544, 545, 999, 1000]:
+        h = O.Keccak256(domain=0x06)
+        h.update(msg[:n])
+        assert h.finalize_reset() == hashlib.sha3_256(msg[:n]).digest(), n
+    h = O.Keccak256(domain=0x06)
+    for a, b in [(0, 1), (1, 137), (137, 138), (138, 600), (600, 1000)]:
+        h.update(msg[a:b])
+    assert h.finalize_reset() == hashlib.sha3_256(msg).digest()
+    # finalize_reset really resets
+    h.update(b"abc")
+    assert h.finalize_reset() == hashlib.sha3_256(b"abc").digest()
+    # and the reference's variant (0x01) on the published vectors
+    assert O.keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    assert O.keccak256(b"abc").hex() == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"
+
+
+def test_field_constants_follow_from_the_curves_public_parameters():
+    """The moduli are not free constants: both scalar fields are r = z^4 - z^2 + 1 of the BLS12 family parameter
+    (BLS12-381: z = -0xd201000000010000, BLS12-377: z = 0x8508c00000000001).  The multiplicative generators ark-ff
+    declares (7, 22) must be quadratic non-residues for g^((r-1)/2^s) to be a PRIMITIVE 2^s-th root of unity, and the
+    2^32-th root derived from 7 is the `ROOT_OF_UNITY` the zkcrypto `bls12_381::Scalar` type publishes for the same
+    generator — a second library agreeing on the NTT's root choice, which the reference's only fft test (a round trip,
+    fft/src/lib.rs:78-82) does not pin."""
+    z381, z377 = -0xD201000000010000, 0x8508C00000000001
+    assert z381**4 - z381**2 + 1 == O.BLS12_381_FR.p
+    assert z377**4 - z377**2 + 1 == O.BLS12_377_FR.p
+    for Fq in (O.BLS12_381_FR, O.BLS12_377_FR):
+        assert pow(Fq.generator, (Fq.p - 1) // 2, Fq.p) == Fq.p - 1
+        w = Fq.get_root_of_unity(1 << Fq.two_adicity)
+        assert pow(w, 1 << (Fq.two_adicity - 1), Fq.p) == Fq.p - 1  # exact order 2^s
+        assert Fq.get_root_of_unity(1 << (Fq.two_adicity + 1)) is None
+    assert (O.BLS12_381_FR.two_adicity, O.BLS12_377_FR.two_adicity) == (32, 47)
+    assert O.BLS12_381_FR.get_root_of_unity(1 << 32) == 0x16A2A19EDFE81F20D09B681922C813B4B63683508C2280B93829971F439F0D2B
