@@ -5,7 +5,7 @@
 //   * the others (product round kernels, folds, generator, single-GPU NTT: shared memory, shuffles, PTX) are
 //     replaced by naive models of their documented contract (kernels.h) — what is exercised there is the caller,
 //     not the kernel: the GPU suite checks the kernels;
-//   * sharded-only launchers return cudaErrorNotSupported.
+//   * the narrowing launch after the sharded all-reduce is modelled too (mock_nccl.cpp provides the collectives).
 // Reducing launches publish like reduce_publish does: result_dev, the mapped host copy, the completion flag.
 #include <cuda_runtime.h>
 
@@ -15,8 +15,9 @@
 #include <vector>
 
 #define __launch_bounds__(...)
-static uint3 threadIdx, blockIdx;
-static dim3 gridDim, blockDim;
+// thread_local: the multi-rank driver runs one rank per thread
+static thread_local uint3 threadIdx, blockIdx;
+static thread_local dim3 gridDim, blockDim;
 
 #include "kernels.h"
 #include "field_f64.cuh"
@@ -24,10 +25,10 @@ static dim3 gridDim, blockDim;
 
 namespace zk {
 namespace {
-const host::Field* g_field = nullptr;
-host::El g_challenge;
-std::vector<host::El> g_sums;
-alignas(32) uint4 sop_smem[2 * 2 * kMaxFactors * 128];
+thread_local const host::Field* g_field = nullptr;
+thread_local host::El g_challenge;
+thread_local std::vector<host::El> g_sums;
+alignas(32) thread_local uint4 sop_smem[2 * 2 * kMaxFactors * 128];
 constexpr int kThreads = 128;
 
 inline host::El el(const Fe& a) { host::El e; std::memcpy(e.v, a.v, 32); return e; }
@@ -264,7 +265,48 @@ cudaError_t launch_deinterleave(const Fe* in, Fe* out, uint64_t local_len, unsig
         for (uint64_t j = 0; j < local_len; j++) out[q * local_len + j] = in[j * world + q];
     return cudaSuccess;
 }
-cudaError_t launch_narrow(int, const uint64_t*, Fe*, Fe*, int, unsigned*, unsigned, cudaStream_t, int*) { return cudaErrorNotSupported; }
+// after the exact u64 all-reduce of one 32-bit limb per lane: carry-propagate, reduce mod p, publish result + flag
+cudaError_t launch_narrow(int field, const uint64_t* lanes, Fe* out_dev, Fe* out_host_devptr, int count, unsigned* flag_host_devptr,
+                          unsigned seq, cudaStream_t, int* launches) {
+    const Field F(field);
+    ++*launches;
+    for (int t = 0; t < count; t++) {
+        // value = sum_i lanes[i] * 2^(32 i), up to ~2^(256+3): reduce by repeated subtraction of p on a 5-word number
+        uint64_t w[5] = {0, 0, 0, 0, 0};
+        unsigned __int128 carry = 0;
+        uint32_t limbs[10] = {0};
+        for (int i = 0; i < 8; i++) {
+            carry += lanes[(size_t)t * 8 + i];
+            limbs[i] = (uint32_t)carry;
+            carry >>= 32;
+        }
+        limbs[8] = (uint32_t)carry;
+        limbs[9] = (uint32_t)(carry >> 32);
+        for (int i = 0; i < 5; i++) w[i] = (uint64_t)limbs[2 * i] | ((uint64_t)limbs[2 * i + 1] << 32);
+        const host::FieldParams& P = host::params(field);
+        auto geq = [&]() {
+            if (w[4]) return true;
+            for (int i = 3; i >= 0; i--)
+                if (w[i] != P.p[i]) return w[i] > P.p[i];
+            return true;
+        };
+        while (geq()) {
+            unsigned __int128 borrow = 0;
+            for (int i = 0; i < 5; i++) {
+                const unsigned __int128 d = (unsigned __int128)w[i] - (i < 4 ? P.p[i] : 0) - (uint64_t)borrow;
+                w[i] = (uint64_t)d;
+                borrow = (d >> 64) & 1;
+            }
+        }
+        Fe v;
+        std::memcpy(v.v, w, 32);
+        out_dev[t] = v;
+        out_host_devptr[t] = v;
+    }
+    if (seq != 0) *flag_host_devptr = seq;
+    (void)F;
+    return cudaSuccess;
+}
 
 // ---- single-GPU NTT: a plain iterative transform with the contract of kernels_ntt.cu, INCLUDING where the result
 // lands (sizes >= 2^6 end up in the plan's scratch buffer, the caller swaps or copies) so that the callers' buffer

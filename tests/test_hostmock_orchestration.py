@@ -7,6 +7,8 @@ contracts.  tests/hostmock_driver.py then drives the library through the Python 
 points at the mock) and compares with the oracle: prove / prove_partial / verify round loops with the derived-S(1)
 claims, the absorb pipeline, evaluate / partial_evaluate chains, the sum-of-products prover, zk_ntt's buffer swap with
 its plan, and the multi-GPU NTT's step functions with 2/4/8 virtual ranks (the path that has not yet run on hardware).
+A second driver (tests/hostmock_sharded_driver.py) runs the SHARDED entry points with every rank a thread and an
+in-process stand-in for NCCL.
 
 TEST INFRASTRUCTURE ONLY: it checks the caller side of every launch.  The product library is untouched by it and keeps
 refusing to run without a GPU (test_abi_host.py::test_no_cpu_fallback_without_gpu)."""
@@ -35,6 +37,9 @@ def _build_hostmock():
     for p, j in zip(procs, jobs):
         out, _ = p.communicate(timeout=600)
         assert p.returncode == 0, " ".join(j) + "\n" + out[-3000:]
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-fvisibility=hidden", "-shared", os.path.join(mock, "mock_nccl.cpp"),
+                        "-o", os.path.join(out_dir, "libnccl.so.2"), "-lpthread"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
     so = os.path.join(ROOT, "build", "libzk_b200_hostmock.so")
     r = subprocess.run(["g++", "-shared", "-o", so] + [os.path.join(out_dir, f) for f in ("api.o", "mock_kernels.o", "mock_cudart.o", "keccak_avx512.o")]
                        + ["-ldl", "-lpthread"], capture_output=True, text=True)
@@ -49,6 +54,21 @@ def test_api_orchestration_against_the_oracle_under_the_host_mock():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     res = json.loads(r.stdout.strip().splitlines()[-1])
     assert res["hostmock_orchestration_ok"] and res["checks"] >= 229 and not res["failures"], res
+
+
+def test_sharded_entry_points_with_ranks_as_threads_under_the_host_mock():
+    """world = 2, 4, 8: every rank a thread with its own sharded context, an in-process NCCL stand-in
+    (tests/cpp/hostmock/mock_nccl.cpp: collectives = thread rendezvous + copies): the sharded ProductPoly and
+    sum-of-products provers (exact all-reduce + narrowing, derived S(1) on rank 0, residual gather at several
+    thresholds) and zk_ntt_sharded's send/recv exchanges — the real api.cu code, every rank checked against the oracle."""
+    so = _build_hostmock()
+    mockdir = os.path.join(ROOT, "build", "mock")
+    env = dict(os.environ, ZK_B200_LIB=so, LD_LIBRARY_PATH=mockdir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "hostmock_sharded_driver.py")], capture_output=True, text=True, env=env,
+                       timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["hostmock_sharded_ok"] and res["checks"] >= 1000 and not res["failures"], res
 
 
 def test_the_host_mock_is_not_reachable_from_the_product():
