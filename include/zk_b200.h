@@ -217,6 +217,13 @@ ZK_API int zk_sumcheck_prove_sop(zk_ctx* ctx, zk_table* const* tables, unsigned 
                                  int absorb_initial_poly, uint64_t* round_polys_out, uint64_t* challenges_out,
                                  uint64_t* final_evals_out);
 
+/* SumcheckVerifier::verify (verifier.rs:15-33) for a proof made by zk_sumcheck_prove_sop with absorb_initial_poly != 0:
+ * absorbs the tables' to_bytes(), replays the rounds, then checks the sub-claim against P(challenges) on the device.
+ * Status codes as zk_sumcheck_verify.  Tables are not modified. */
+ZK_API int zk_sumcheck_verify_sop(zk_ctx* ctx, const zk_table* const* tables, unsigned n_tables, const uint8_t* term_len,
+                                  const uint8_t* term_factors, unsigned n_terms, const uint64_t sum[4],
+                                  const uint64_t* round_polys, unsigned n_rounds, unsigned degree);
+
 /* ---- transcript  (transcript/src/lib.rs) — host Keccak-256 -------------------------------------- */
 ZK_API zk_transcript* zk_transcript_new(void);                                             /* :10 */
 ZK_API void zk_transcript_free(zk_transcript* t);

@@ -294,6 +294,19 @@ struct SumcheckVerifier {  // sumcheck/src/verifier.rs:9-79
         check(st);
         return true;
     }
+    // the same for a sum of products proved with SumcheckProver::prove (zk_sumcheck_verify_sop)
+    static bool verify(const SumOfProductsPoly<F>& poly, const SumcheckProof<F>& proof) {
+        std::vector<F> flat;
+        size_t np = proof.round_polys.empty() ? 1 : proof.round_polys[0].size();
+        for (auto& r : proof.round_polys) flat.insert(flat.end(), r.begin(), r.end());
+        auto h = poly.handles();
+        int st = zk_sumcheck_verify_sop(Context::instance().get(), (const zk_table* const*)h.data(), (unsigned)h.size(), poly.term_len().data(),
+                                        poly.term_factors().data(), (unsigned)poly.term_len().size(), proof.sum.limbs.data(),
+                                        flat.empty() ? nullptr : flat[0].limbs.data(), (unsigned)proof.round_polys.size(), (unsigned)np - 1);
+        if (st == ZK_VERIFY_FALSE) return false;
+        check(st);
+        return true;
+    }
     static SubClaim<F> verify_partial(const SumcheckProof<F>& proof) {  // :38-41
         std::vector<F> flat;
         size_t np = proof.round_polys.empty() ? 1 : proof.round_polys[0].size();

@@ -78,6 +78,25 @@ impl<F: PrimeField> SumOfProductsPoly<F> {
         self.polynomials.iter().flat_map(|p| p.to_bytes()).collect()
     }
 
+    /// `SumcheckVerifier::verify` for P (sumcheck/src/verifier.rs:15-33): Ok(true) / Ok(false) / the reference's errors.
+    pub(crate) fn verify(&self, sum: &F, round_polys: &[Vec<F>]) -> Result<bool, &'static str> {
+        let tables = self.upload_all()?;
+        let handles: Vec<*const sys::zk_table> = tables.iter().map(|t| t.0 as *const _).collect();
+        let flat: Vec<F> = round_polys.iter().flatten().copied().collect();
+        let degree = round_polys.first().map_or(0, |r| r.len().saturating_sub(1)) as u32;
+        let st = unsafe {
+            sys::zk_sumcheck_verify_sop(
+                sys::ctx(), handles.as_ptr(), handles.len() as u32, self.term_len.as_ptr(), self.term_factors.as_ptr(),
+                self.term_len.len() as u32, sum as *const F as *const u64, sys::as_limbs(&flat), round_polys.len() as u32, degree,
+            )
+        };
+        match st {
+            sys::ZK_OK => Ok(true),
+            sys::ZK_VERIFY_FALSE => Ok(false),
+            _ => Err(sys::status_to_err(st)),
+        }
+    }
+
     /// Round polynomials and challenges of the sumcheck over P (the reference's loop, sumcheck/src/prover.rs:33-73).
     pub(crate) fn prove(&self, degree: u32, sum: &F, absorb: bool) -> Result<(Vec<Vec<F>>, Vec<F>), &'static str> {
         let tables = self.upload_all()?; // consumed by the library, freed on drop

@@ -29,6 +29,12 @@ impl<const MAX_VAR_DEGREE: u8, F: PrimeField> SumcheckProver<MAX_VAR_DEGREE, F> 
         Ok((SumcheckProof { sum, round_polys }, challenges))
     }
 
+    /// `prove` over a sum of products: absorbs the tables' `to_bytes()` first.
+    pub fn prove_sum_of_products(poly: SumOfProductsPoly<F>, sum: F) -> Result<SumcheckProof<F>, &'static str> {
+        let (round_polys, _) = poly.prove(MAX_VAR_DEGREE as u32, &sum, true)?;
+        Ok(SumcheckProof { sum, round_polys })
+    }
+
     /// The same loop over a sum of products (`zk_sumcheck_prove_sop`).
     pub fn prove_partial_sum_of_products(
         poly: SumOfProductsPoly<F>,

@@ -39,6 +39,17 @@ impl<F: PrimeField> SumcheckVerifier<F> {
         }
     }
 
+    /// The same for a sum of products proved with `SumcheckProver::prove_sum_of_products` (`zk_sumcheck_verify_sop`).
+    pub fn verify_sum_of_products(
+        poly: crate::sum_of_products::SumOfProductsPoly<F>,
+        proof: SumcheckProof<F>,
+    ) -> Result<bool, &'static str> {
+        if proof.round_polys.len() != poly.n_vars() {
+            return Err("invalid proof: require 1 round poly for each variable in poly");
+        }
+        poly.verify(&proof.sum, &proof.round_polys)
+    }
+
     /// :38-41 — host only.
     pub fn verify_partial(proof: SumcheckProof<F>) -> Result<SubClaim<F>, &'static str> {
         let field = sys::field_id_of::<F>().ok_or(crate::UNSUPPORTED_FIELD)?;

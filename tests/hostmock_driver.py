@@ -126,7 +126,28 @@ def main():
     rsum = cref.sop_sum(0, refs, GKR, 5)
     rp, _, _ = cref.prove_sop(0, refs, GKR, 5, 3, rsum, absorb=True)
     sp = zk.SumOfProductsPoly.new([zk.MultiLinearPolynomial.new(5, r, ctx=ctx) for r in refs], GKR)
-    check((zk.SumcheckProver(3).prove(sp, zk.from_mont(0, rsum)[0])._round_polys_mont == rp).all(), "sop prove with absorb")
+    keep = sp.clone()
+    proof = zk.SumcheckProver(3).prove(sp, zk.from_mont(0, rsum)[0])
+    check((proof._round_polys_mont == rp).all(), "sop prove with absorb")
+    check(zk.SumcheckVerifier.verify(keep, proof) is True, "sop verify accepts")
+    tampered = zk.SumOfProductsPoly.new([zk.MultiLinearPolynomial.new(5, r, ctx=ctx) for r in [refs[1], refs[0], refs[2], refs[3]]], GKR)
+    try:  # other bytes absorbed -> other challenges: round 0 still passes (it only involves the claimed sum), round 1 cannot
+        zk.SumcheckVerifier.verify(tampered, proof)
+        check(False, "sop verify: other tables must be rejected")
+    except zk.ZkError as e:
+        check(e.status == 7, ("sop verify: other tables status", e.status))
+    bad_rounds = zk.SumcheckProof.from_values(0, proof.sum, proof.round_polys[:-1])
+    try:
+        zk.SumcheckVerifier.verify(keep, bad_rounds)
+        check(False, "sop verify: round count")
+    except zk.ZkError as e:
+        check(e.status == 5, ("sop verify: round count status", e.status))
+    wrong = zk.SumcheckProof.from_values(0, proof.sum + 1, proof.round_polys)
+    try:
+        zk.SumcheckVerifier.verify(keep, wrong)
+        check(False, "sop verify: wrong sum")
+    except zk.ZkError as e:
+        check(e.status == 7, ("sop verify: wrong sum status", e.status))
 
     # ---- NTT: single-GPU entry (buffer swap with the plan), then the multi-GPU step functions with virtual ranks
     for fid in (0, 1):

@@ -481,8 +481,12 @@ class SumcheckVerifier:
     def verify(poly: ProductPoly, proof: SumcheckProof) -> bool:  # :15-33
         rp = np.ascontiguousarray(proof._round_polys_mont)
         d1 = rp.shape[1] if rp.ndim == 3 else 1
-        st = lib().zk_sumcheck_verify(poly.ctx.h, poly._arr(), len(poly.polynomials), proof._sum_mont.ctypes.data,
-                                      rp.ctypes.data if rp.size else None, rp.shape[0], d1 - 1)
+        if isinstance(poly, SumOfProductsPoly):
+            st = lib().zk_sumcheck_verify_sop(poly.ctx.h, poly._arr(), len(poly.polynomials), *poly._terms(), proof._sum_mont.ctypes.data,
+                                              rp.ctypes.data if rp.size else None, rp.shape[0], d1 - 1)
+        else:
+            st = lib().zk_sumcheck_verify(poly.ctx.h, poly._arr(), len(poly.polynomials), proof._sum_mont.ctypes.data,
+                                          rp.ctypes.data if rp.size else None, rp.shape[0], d1 - 1)
         if st == 8:  # ZK_VERIFY_FALSE == Ok(false)
             return False
         poly.ctx.check(st)

@@ -76,6 +76,7 @@ SIGNATURES = {
     "zk_sop_evaluate": (C.c_int, [vp, vpp, C.c_uint, vp, vp, C.c_uint, vp, C.c_uint, vp]),
     "zk_sop_combine": (C.c_int, [C.c_int, vp, vp, C.c_uint, vp, C.c_uint, vp]),
     "zk_sumcheck_prove_sop": (C.c_int, [vp, vpp, C.c_uint, vp, vp, C.c_uint, C.c_uint, vp, C.c_int, vp, vp, vp]),
+    "zk_sumcheck_verify_sop": (C.c_int, [vp, vpp, C.c_uint, vp, vp, C.c_uint, vp, vp, C.c_uint, C.c_uint]),
     "zk_transcript_new": (vp, []),
     "zk_transcript_free": (None, [vp]),
     "zk_transcript_append": (None, [vp, C.c_char_p, C.c_size_t]),

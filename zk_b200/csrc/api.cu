@@ -1276,6 +1276,32 @@ int zk_sumcheck_verify(zk_ctx* ctx, const zk_table* const* tables, unsigned m, c
     return ZK_OK;
 }
 
+int zk_sumcheck_verify_sop(zk_ctx* ctx, const zk_table* const* tables, unsigned n_tables, const uint8_t* term_len,
+                           const uint8_t* term_factors, unsigned n_terms, const uint64_t sum[4], const uint64_t* round_polys,
+                           unsigned n_rounds, unsigned degree) {
+    if (!ctx || !sum || (n_rounds && !round_polys)) return fail(ctx, ZK_ERR_INVALID_ARG);
+    zk::SopSpec spec;
+    int st = sop_spec_from(ctx, tables, n_tables, term_len, term_factors, n_terms, &spec);
+    if (st != ZK_OK) return st;
+    if (degree > ZK_MAX_DEGREE) return fail(ctx, ZK_ERR_UNSUPPORTED, "degree > ZK_MAX_DEGREE");
+    if (n_rounds != tables[0]->n_vars) return fail(ctx, ZK_ERR_PROOF_ROUNDS);  // verifier.rs:17-19
+    CU(ctx, cudaSetDevice(ctx->device));
+    Field F(tables[0]->field);
+    zk::host::Transcript tr;
+    st = absorb_tables(ctx, tables, n_tables, tr);  // :21-22, the tables' to_bytes() in tables[] order
+    count(ctx);
+    if (st != ZK_OK) return st;
+    El sub;
+    std::vector<uint64_t> challenges((size_t)n_rounds * 4 + 4);
+    st = verify_internal(F, tr, sum, round_polys, n_rounds, degree, &sub, challenges.data());
+    if (st != ZK_OK) return fail(ctx, st);
+    uint64_t ev[4];
+    st = zk_sop_evaluate(ctx, tables, n_tables, term_len, term_factors, n_terms, challenges.data(), n_rounds, ev);  // :28-30
+    if (st != ZK_OK) return fail(ctx, ZK_ERR_INITIAL_EVAL);
+    if (el_from(ev) != sub) return fail(ctx, ZK_VERIFY_FALSE);  // :32
+    return ZK_OK;
+}
+
 int zk_sumcheck_proof_dump(int field, const uint64_t sum[4], const uint64_t* round_polys, unsigned n_rounds,
                            unsigned degree, const uint64_t* challenges, const uint64_t* final_evals, unsigned m,
                            uint8_t* out, size_t out_cap, size_t* out_len, uint8_t digest_out[32]) {
