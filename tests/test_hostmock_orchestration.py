@@ -71,6 +71,24 @@ def test_sharded_entry_points_with_ranks_as_threads_under_the_host_mock():
     assert res["hostmock_sharded_ok"] and res["checks"] >= 1000 and not res["failures"], res
 
 
+def test_gpu_suite_files_replayed_under_the_host_mock():
+    """The GPU suite's own test files (the reference's tests re-expressed, the parity cases, the sum-of-products and NTT
+    cases) run in a child pytest with the host mock loaded instead of the product library: every argument check, status
+    code, error string, buffer hand-over and round loop those tests drive is executed here on the CPU through the real
+    api.cu.  (Only the 2^22+ cases are deselected: the mock's arithmetic is word-serial host code.)  This does NOT
+    replace the GPU run — the kernels are stand-ins here; it makes sure a red GPU suite can only mean a kernel problem."""
+    so = _build_hostmock()
+    mockdir = os.path.join(ROOT, "build", "mock")
+    env = dict(os.environ, ZK_B200_LIB=so, LD_LIBRARY_PATH=mockdir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    files = [os.path.join(ROOT, "tests", f) for f in ("test_gpu_reference_kats.py", "test_gpu_sop.py", "test_gpu_parity.py", "test_gpu_ntt.py")]
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", "-k",
+           "not large_prove_self_consistency and not large_roundtrip and not multi_chunk"] + files
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1500, cwd=ROOT)
+    tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
+    assert r.returncode == 0 and " passed" in tail and "failed" not in tail, r.stdout[-3000:] + r.stderr[-2000:]
+    assert int(tail.split(" passed")[0].split()[-1]) >= 80, tail
+
+
 def test_the_host_mock_is_not_reachable_from_the_product():
     """Nothing under zk_b200/ (the product) or in the Makefile mentions the mock; only an explicit ZK_B200_LIB does."""
     for base, _, files in os.walk(os.path.join(ROOT, "zk_b200")):
