@@ -48,6 +48,7 @@ template <class F> void fe_fold_fixed_f64_x2(Fe& lo, Fe& hi, const Fe& x0, const
 inline Fe ld_fe(const Fe* p) { return *p; }
 inline Fe ld_fe_stream(const Fe* p) { return *p; }
 inline void st_fe(Fe* p, const Fe& v) { *p = v; }
+#include "../host_accw.hpp"
 struct ReduceArgs { int skip1; };
 template <class F, int NP>
 void reduce_publish(const Fe* acc, const ReduceArgs&) {
@@ -172,8 +173,8 @@ cudaError_t sop_replay(int field, const TablePtrs& tabs, const SopSpec& spec, ui
     g_sums.assign((size_t)D + 1, F.zero());
     const unsigned grid = 3;
     const int skip1 = (fold && claim) ? 1 : 0;
-    if (fold) replay(grid, kThreads, [&] { sop_round_kernel<FT, D, true, false>(tabs, spec, q, FixedMul{}, FixedMulF64Sel{}, ReduceArgs{skip1}); });
-    else replay(grid, kThreads, [&] { sop_round_kernel<FT, D, false, false>(tabs, spec, q, FixedMul{}, FixedMulF64Sel{}, ReduceArgs{0}); });
+    if (fold) replay(grid, kThreads, [&] { sop_round_kernel<FT, D, true, false, false>(tabs, spec, q, FixedMul{}, FixedMulF64Sel{}, ReduceArgs{skip1}); });
+    else replay(grid, kThreads, [&] { sop_round_kernel<FT, D, false, false, false>(tabs, spec, q, FixedMul{}, FixedMulF64Sel{}, ReduceArgs{0}); });
     if (skip1) g_sums[1] = F.sub(el(*claim), g_sums[0]);
     publish(s, g_sums);
     g_field = nullptr;

@@ -5,7 +5,7 @@
 // word-serial Montgomery arithmetic, shared memory is an ordinary array, and the grid is replayed block by block,
 // thread by thread.  What this pins without a GPU: the pair / quadruple index conventions of the fused in-place
 // fold (evaluation_form.rs:40-80 with initial_var = 0), the term bookkeeping, the evaluation points t = 0..D, the
-// grid-stride loop with ragged sizes.  What it cannot pin (the PTX multiplier, the block/grid reduction) is shared
+// grid-stride loop with ragged sizes, the deferred-reduction (WIDE) variant's shared-memory carve-up and term handling.  What it cannot pin (the PTX multiplier, the block/grid reduction) is shared
 // with the product kernels and covered by the GPU suite.
 // The expected values come from an independent, deliberately naive model written below: fold out of place, then
 // evaluate every term at every t from scratch with multiplications by t.
@@ -31,7 +31,10 @@ constexpr int kThreads = 128;
 const host::Field* g_field = nullptr;
 host::El g_challenge;                       // the launch-wide fold multiplier (the device reads it from FixedMul)
 std::vector<host::El> g_sums;               // what reduce_publish would publish
-alignas(32) uint4 sop_smem[2 * 2 * kMaxFactors * kThreads];
+// shared memory of one block, sized by the harness exactly as the launcher does (kernels_sop.cu: sop_smem_total) and
+// followed by guard words: a carve-up that runs past the launch's allocation is caught
+constexpr size_t kSmemMaxUint4 = 2 * 2 * kMaxFactors * kThreads + 5 * (4 * kThreads + kThreads / 4) + 64;
+alignas(32) uint4 sop_smem[kSmemMaxUint4];
 
 inline host::El el(const Fe& a) { host::El e; std::memcpy(e.v, a.v, 32); return e; }
 inline Fe fe(const host::El& e) { Fe a; std::memcpy(a.v, e.v, 32); return a; }
@@ -49,6 +52,7 @@ template <class F> void fe_fold_fixed_f64_x2(Fe& lo, Fe& hi, const Fe& x0, const
     lo = fe_fold_fixed<F>(x0, x2, FixedMul{});
     hi = fe_fold_fixed<F>(x1, x3, FixedMul{});
 }
+#include "host_accw.hpp"
 struct ReduceArgs { int skip1; };
 template <class F, int NP>
 void reduce_publish(const Fe* acc, const ReduceArgs&) {  // the harness applies S(1) = claim - S(0) after the last block
@@ -76,16 +80,24 @@ static El rnd_el(const Field& F) {  // a product of two random words times a thi
     return F.add(F.mul(F.mul(a, b), F.mul(c, b)), a);
 }
 
-template <class FT, int D, bool FOLD, bool F64>
+static long g_guard_hits = 0;
+template <class FT, int D, bool FOLD, bool F64, bool WIDE>
 static void replay(const zk::TablePtrs& tabs, const zk::SopSpec& spec, uint64_t q, unsigned grid, int skip1) {
     gridDim = dim3(grid, 1, 1);
     blockDim = dim3(zk::kThreads, 1, 1);
-    for (unsigned b = 0; b < grid; b++)
+    // what the launcher allocates for this launch, in uint4 units
+    const size_t used = ((size_t)2 * spec.n_tables * zk::kThreads * sizeof(zk::Fe) + (WIDE ? zk::accw_bytes(D + 1) : 0)) / sizeof(uint4);
+    for (unsigned b = 0; b < grid; b++) {
+        // a block starts with whatever the previous one left behind, except that the kernel's own accw_zero +
+        // __syncthreads() happen before any accumulation: in this sequential replay that is a clear before the block
+        for (size_t i = 0; i < zk::kSmemMaxUint4; i++) zk::sop_smem[i] = (i < used) ? uint4{0, 0, 0, 0} : uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu};
         for (unsigned t = 0; t < (unsigned)zk::kThreads; t++) {
             blockIdx = uint3{b, 0, 0};
             threadIdx = uint3{t, 0, 0};
-            zk::sop_round_kernel<FT, D, FOLD, F64>(tabs, spec, q, zk::FixedMul{}, zk::FixedMulF64Sel{}, zk::ReduceArgs{skip1});
+            zk::sop_round_kernel<FT, D, FOLD, F64, WIDE>(tabs, spec, q, zk::FixedMul{}, zk::FixedMulF64Sel{}, zk::ReduceArgs{skip1});
         }
+        for (size_t i = used; i < zk::kSmemMaxUint4; i++) g_guard_hits += (zk::sop_smem[i].x != 0xDEADBEEFu || zk::sop_smem[i].w != 0xDEADBEEFu);
+    }
 }
 
 template <class FT, int D>
@@ -137,11 +149,14 @@ static long run_case(int field, unsigned log_len, bool fold, const zk::SopSpec& 
         tabs.t[k] = dev[(size_t)k].data();
     }
     zk::g_sums.assign((size_t)D + 1, F.zero());
-    // mode 0: every evaluation summed, integer folds; 1: S(1) derived from the claim; 2: S(1) derived, FP64 folds
-    if (fold && mode == 2) replay<FT, D, true, true>(tabs, spec, len / 4, grid, 1);
-    else if (fold) replay<FT, D, true, false>(tabs, spec, len / 4, grid, mode == 1);
-    else replay<FT, D, false, false>(tabs, spec, len / 2, grid, 1 /* ignored without a fold */);
-    if (fold && mode >= 1) {  // what the last block does with ra.claim = S(0) + S(1)
+    // mode 0: every evaluation summed, integer folds; 1: S(1) derived from the claim; 2: S(1) derived, FP64 folds;
+    // 3: deferred reduction (WIDE), every evaluation summed; 4: WIDE with S(1) derived
+    if (fold && mode == 2) replay<FT, D, true, true, false>(tabs, spec, len / 4, grid, 1);
+    else if (fold && mode >= 3) replay<FT, D, true, false, true>(tabs, spec, len / 4, grid, mode == 4);
+    else if (fold) replay<FT, D, true, false, false>(tabs, spec, len / 4, grid, mode == 1);
+    else if (mode >= 3) replay<FT, D, false, false, true>(tabs, spec, len / 2, grid, 1);
+    else replay<FT, D, false, false, false>(tabs, spec, len / 2, grid, 1 /* ignored without a fold */);
+    if (fold && (mode == 1 || mode == 2 || mode == 4)) {  // what the last block does with ra.claim = S(0) + S(1)
         long untouched = (zk::g_sums[1] != F.zero());
         zk::g_sums[1] = F.sub(F.add(want[0], want[1]), zk::g_sums[0]);
         if (untouched) return 1000000;  // the t = 1 products were not skipped
@@ -177,7 +192,8 @@ int main() {
             for (int fold = 0; fold < 2; fold++) {
                 if (fold && log_len < 2) continue;  // the fused launch needs 4 entries
                 for (unsigned grid : {1u, 3u})
-                    for (int mode = 0; mode < (fold ? 3 : 1); mode++) {
+                    for (int mode = 0; mode < 5; mode++) {
+                        if (!fold && mode != 0 && mode != 3) continue;
                         if (field == 0) {
                             bad += run_case<zk::Fr381, 3>(field, log_len, fold, gkr, grid, mode);
                             bad += run_case<zk::Fr381, 2>(field, log_len, fold, sq, grid, mode);
@@ -196,6 +212,6 @@ int main() {
             }
         }
     }
-    std::printf("%ld cases, %ld mismatches\n", cases, bad);
-    return bad ? 1 : 0;
+    std::printf("%ld cases, %ld mismatches, %ld guard hits\n", cases, bad, g_guard_hits);
+    return (bad || g_guard_hits) ? 1 : 0;
 }

@@ -20,6 +20,7 @@
 
 #include "kernels.h"
 #include "reduce.cuh"
+#include "accw.cuh"
 #include "sop_kernel.cuh"
 
 namespace zk {
@@ -27,18 +28,20 @@ namespace {
 
 constexpr size_t sop_smem_bytes(int n_tables) { return (size_t)2 * n_tables * kThreads * sizeof(Fe); }
 
-template <class F, int D, bool FOLD, bool F64>
+constexpr size_t sop_smem_total(int n_tables, int np, bool wide) { return sop_smem_bytes(n_tables) + (wide ? accw_bytes(np) : 0); }
+
+template <class F, int D, bool FOLD, bool F64, bool WIDE>
 cudaError_t do_sop_v(const TablePtrs& tabs, const SopSpec& spec, uint64_t q, const Fe& r, const ReduceScratch& s,
                      cudaStream_t st, const Fe* claim) {
-    static const cudaError_t attr = cudaFuncSetAttribute(sop_round_kernel<F, D, FOLD, F64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         (int)sop_smem_bytes(kMaxFactors));
+    static const cudaError_t attr = cudaFuncSetAttribute(sop_round_kernel<F, D, FOLD, F64, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)sop_smem_total(kMaxFactors, D + 1, WIDE));
     if (attr != cudaSuccess) return attr;
-    const size_t smem = sop_smem_bytes(spec.n_tables);
+    const size_t smem = sop_smem_total(spec.n_tables, D + 1, WIDE);
     static int bpsm_cache[kMaxFactors + 1] = {0};
     int& bpsm = bpsm_cache[spec.n_tables];
     if (bpsm == 0) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sop_round_kernel<F, D, FOLD, F64>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sop_round_kernel<F, D, FOLD, F64, WIDE>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
         bpsm = nb;
     }
     const unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
@@ -49,11 +52,11 @@ cudaError_t do_sop_v(const TablePtrs& tabs, const SopSpec& spec, uint64_t q, con
         ra.skip1 = 1;
         ra.claim = *claim;
     }
-    sop_round_kernel<F, D, FOLD, F64><<<grid, kThreads, smem, st>>>(tabs, spec, q, tab, tab64, ra);
+    sop_round_kernel<F, D, FOLD, F64, WIDE><<<grid, kThreads, smem, st>>>(tabs, spec, q, tab, tab64, ra);
     return cudaGetLastError();
 }
 
-// Which pipe folds: ZK_B200_SOP_FOLD_PIPE=int|f64 (default int until the FP64 variant has been measured on this kernel)
+// Which pipe folds: ZK_B200_SOP_FOLD_PIPE=int|f64 (default int: the FP64 variant measured 6 % slower on the GKR shape)
 inline bool sop_fold_on_f64() {
     static const bool on = [] {
         const char* e = std::getenv("ZK_B200_SOP_FOLD_PIPE");
@@ -61,12 +64,22 @@ inline bool sop_fold_on_f64() {
     }();
     return on;
 }
+// ZK_B200_SOP_WIDE=1: deferred reduction of every term's last product (default off: written after the round's GPU
+// budget was spent — replayed on the host, not yet measured or run on hardware)
+inline bool sop_wide() {
+    static const bool on = [] {
+        const char* e = std::getenv("ZK_B200_SOP_WIDE");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
 
 template <class F, int D, bool FOLD>
 cudaError_t do_sop(const TablePtrs& tabs, const SopSpec& spec, uint64_t q, const Fe& r, const ReduceScratch& s,
                    cudaStream_t st, const Fe* claim) {
-    if (FOLD && sop_fold_on_f64()) return do_sop_v<F, D, FOLD, FOLD>(tabs, spec, q, r, s, st, claim);
-    return do_sop_v<F, D, FOLD, false>(tabs, spec, q, r, s, st, claim);
+    if (sop_wide()) return do_sop_v<F, D, FOLD, false, true>(tabs, spec, q, r, s, st, claim);
+    if (FOLD && sop_fold_on_f64()) return do_sop_v<F, D, FOLD, FOLD, false>(tabs, spec, q, r, s, st, claim);
+    return do_sop_v<F, D, FOLD, false, false>(tabs, spec, q, r, s, st, claim);
 }
 
 template <class F, bool FOLD>
