@@ -49,7 +49,8 @@ def main():
                           "first_round_ms": first, "alg_gbs": alg_bytes / (tot * 1e-3) / 1e9,
                           "first_fused_step_gbs": 48 * nt * (1 << n) / (first[1] * 1e-3) / 1e9 if len(first) > 1 else None,
                           "verified_against_evaluate": bool(ok),
-                          "fold_pipe": os.environ.get("ZK_B200_SOP_FOLD_PIPE", "default")}), flush=True)
+                          "fold_pipe": os.environ.get("ZK_B200_SOP_FOLD_PIPE", "default"),
+                          "deferred_reduction": os.environ.get("ZK_B200_SOP_WIDE", "0") == "1"}), flush=True)
         del poly, tabs
 
 
