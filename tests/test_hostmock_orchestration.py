@@ -89,6 +89,23 @@ def test_gpu_suite_files_replayed_under_the_host_mock():
     assert int(tail.split(" passed")[0].split()[-1]) >= 80, tail
 
 
+def test_cpp_mirror_runs_under_the_host_mock():
+    """include/zk_b200.hpp (the compiled-language mirror of the reference API) executed on the CPU: the reference's tests
+    re-expressed in C++ (tests/cpp/test_reference_kats.cpp, the GPU suite runs the same binary against the product) and
+    the GKR layer through SumOfProductsPoly / SumcheckProver / SumcheckVerifier (tests/cpp/test_sop_mirror_compiles.cpp run)."""
+    so = _build_hostmock()
+    libdir = os.path.dirname(so)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "build", "mock") + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    for src, args, want in (("test_reference_kats.cpp", [], "ALL C++ MIRROR TESTS PASSED"), ("test_sop_mirror_compiles.cpp", ["run"], "GKR LAYER OK")):
+        exe = os.path.join(ROOT, "build", "mock", src.replace(".cpp", "_mock"))
+        cmd = ["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", src), "-L", libdir,
+               "-lzk_b200_hostmock", f"-Wl,-rpath,{libdir}", "-o", exe]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+        r = subprocess.run([exe] + args, capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0 and want in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_the_host_mock_is_not_reachable_from_the_product():
     """Nothing under zk_b200/ (the product) or in the Makefile mentions the mock; only an explicit ZK_B200_LIB does."""
     for base, _, files in os.walk(os.path.join(ROOT, "zk_b200")):
