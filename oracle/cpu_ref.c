@@ -21,6 +21,7 @@
  */
 #include <stdint.h>
 #include <stdlib.h>
+#include <pthread.h>
 #include <string.h>
 
 typedef unsigned __int128 u128;
@@ -370,6 +371,75 @@ EXPORT int zko_prove_fast(int field, uint64_t *const *tables, unsigned m, unsign
             fe *T = (fe *)tables[k];
             for (size_t j = 0; j < half; j++) { fe d = f_sub(&T[j], &T[j + half], F); fe x = f_mul(&r, &d, F); T[j] = f_sub(&T[j], &x, F); }
         }
+        nv--;
+    }
+    if (finals_out) for (unsigned k = 0; k < m; k++) memcpy(finals_out + 4 * k, tables[k], 32);
+    return 0;
+}
+
+/* The streamlined prover on several host cores (pthreads over the pairs of a round; modular sums are order
+ * independent, so the proof is bit-identical).  Reported by bench.py NEXT TO the single-threaded reference-shaped number
+ * as "what a multi-core CPU port of the same algorithm does" — the reference itself is single-threaded. */
+typedef struct {
+    const field_t *F; uint64_t *const *tables; unsigned m, degree; long half, lo, hi; fe r; fe loc[16];
+} mt_job;
+static void *mt_sum_worker(void *arg) {
+    mt_job *J = (mt_job *)arg; const field_t *F = J->F;
+    for (unsigned t = 0; t <= J->degree; t++) J->loc[t] = f_zero();
+    for (long j = J->lo; j < J->hi; j++) {
+        fe e[8], d[8];
+        for (unsigned k = 0; k < J->m; k++) { fe *T = (fe *)J->tables[k]; e[k] = T[j]; d[k] = f_sub(&T[j + J->half], &T[j], F); }
+        for (unsigned t = 0; t <= J->degree; t++) {
+            fe pr = e[0];
+            for (unsigned k = 1; k < J->m; k++) pr = f_mul(&pr, &e[k], F);
+            J->loc[t] = f_add(&J->loc[t], &pr, F);
+            for (unsigned k = 0; k < J->m; k++) e[k] = f_add(&e[k], &d[k], F);
+        }
+    }
+    return NULL;
+}
+static void *mt_fold_worker(void *arg) {
+    mt_job *J = (mt_job *)arg; const field_t *F = J->F;
+    for (unsigned k = 0; k < J->m; k++) {
+        fe *T = (fe *)J->tables[k];
+        for (long j = J->lo; j < J->hi; j++) { fe d = f_sub(&T[j], &T[j + J->half], F); fe x = f_mul(&J->r, &d, F); T[j] = f_sub(&T[j], &x, F); }
+    }
+    return NULL;
+}
+static void mt_run(void *(*fn)(void *), mt_job *jobs, int n_jobs) {
+    pthread_t th[64];
+    for (int i = 1; i < n_jobs; i++) pthread_create(&th[i], NULL, fn, &jobs[i]);
+    fn(&jobs[0]);
+    for (int i = 1; i < n_jobs; i++) pthread_join(th[i], NULL);
+}
+EXPORT int zko_prove_fast_mt(int field, uint64_t *const *tables, unsigned m, unsigned n_vars, unsigned degree,
+                             const uint64_t sum[4], uint64_t *round_polys_out, uint64_t *challenges_out,
+                             uint64_t *finals_out, int n_threads) {
+    const field_t *F = &FIELDS[field];
+    if (m > 8 || degree > 15 || n_threads < 1 || n_threads > 64) return -1;
+    keccak_t tr; k_init(&tr);
+    uint8_t be[32]; fe s; memcpy(s.v, sum, 32); f_to_be32(&s, be, F); k_update(&tr, be, 32);
+    unsigned nv = n_vars;
+    mt_job jobs[64];
+    for (unsigned round = 0; round < n_vars; round++) {
+        const long half = (long)1 << (nv - 1);
+        const int nj = half >= 4096 ? n_threads : 1;   /* small rounds: thread start-up would dominate */
+        for (int i = 0; i < nj; i++) {
+            jobs[i].F = F; jobs[i].tables = tables; jobs[i].m = m; jobs[i].degree = degree; jobs[i].half = half;
+            jobs[i].lo = half * i / nj; jobs[i].hi = half * (i + 1) / nj;
+        }
+        mt_run(mt_sum_worker, jobs, nj);
+        fe acc[16];
+        for (unsigned t = 0; t <= degree; t++) {
+            acc[t] = f_zero();
+            for (int i = 0; i < nj; i++) acc[t] = f_add(&acc[t], &jobs[i].loc[t], F);
+            memcpy(round_polys_out + 4 * ((size_t)round * (degree + 1) + t), acc[t].v, 32);
+            f_to_be32(&acc[t], be, F); k_update(&tr, be, 32);
+        }
+        fe r = t_sample(&tr, F);
+        memcpy(challenges_out + 4 * (size_t)round, r.v, 32);
+        for (int i = 0; i < nj; i++) jobs[i].r = r;
+        mt_run(mt_fold_worker, jobs, nj);
         nv--;
     }
     if (finals_out) for (unsigned k = 0; k < m; k++) memcpy(finals_out + 4 * k, tables[k], 32);

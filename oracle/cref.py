@@ -33,6 +33,7 @@ def lib():
         _lib = C.CDLL(_SO)
         _lib.zko_prove.restype = C.c_int
         _lib.zko_prove_fast.restype = C.c_int
+        _lib.zko_prove_fast_mt.restype = C.c_int
         _lib.zko_prove_sop.restype = C.c_int
         _lib.zko_sop_sum.restype = C.c_int
         _lib.zko_verify_internal.restype = C.c_int
@@ -114,7 +115,7 @@ def product_sum(field: int, tables, n_vars: int) -> np.ndarray:
     return out
 
 
-def prove(field: int, tables, n_vars: int, degree: int, sum_mont: np.ndarray, absorb: bool, fast: bool = False):
+def prove(field: int, tables, n_vars: int, degree: int, sum_mont: np.ndarray, absorb: bool, fast: bool = False, threads: int = 0):
     """Returns (round_polys (n_vars, degree+1, 4), challenges (n_vars, 4), finals (m, 4)), Montgomery limbs."""
     m = len(tables)
     rp = np.zeros((n_vars, degree + 1, 4), dtype=np.uint64)
@@ -124,7 +125,10 @@ def prove(field: int, tables, n_vars: int, degree: int, sum_mont: np.ndarray, ab
     if fast:
         assert not absorb
         work = [t.copy() for t in tables]
-        rc = lib().zko_prove_fast(field, _ptr_array(work), m, n_vars, degree, _p(sum_mont), _p(rp), _p(ch), _p(fin))
+        if threads > 0:  # the streamlined prover on `threads` cores (pthreads), bit-identical
+            rc = lib().zko_prove_fast_mt(field, _ptr_array(work), m, n_vars, degree, _p(sum_mont), _p(rp), _p(ch), _p(fin), int(threads))
+        else:
+            rc = lib().zko_prove_fast(field, _ptr_array(work), m, n_vars, degree, _p(sum_mont), _p(rp), _p(ch), _p(fin))
     else:
         rc = lib().zko_prove(field, _ptr_array(tables), m, n_vars, degree, _p(sum_mont), int(bool(absorb)), _p(rp), _p(ch),
                              _p(fin))

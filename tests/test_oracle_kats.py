@@ -325,3 +325,15 @@ def test_field_constants_follow_from_the_curves_public_parameters():
         assert Fq.get_root_of_unity(1 << (Fq.two_adicity + 1)) is None
     assert (O.BLS12_381_FR.two_adicity, O.BLS12_377_FR.two_adicity) == (32, 47)
     assert O.BLS12_381_FR.get_root_of_unity(1 << 32) == 0x16A2A19EDFE81F20D09B681922C813B4B63683508C2280B93829971F439F0D2B
+
+
+def test_multithreaded_streamlined_prover_is_bit_identical(cref):
+    """oracle/cpu_ref.c::zko_prove_fast_mt (bench.py's `streamlined_all_cores` CPU figure): same proof as the
+    single-threaded provers, whatever the thread count (modular sums are order independent)."""
+    for fid, n, m, d in [(0, 14, 3, 3), (1, 13, 2, 2), (0, 12, 1, 1)]:
+        tabs = [cref.gen_table(fid, 9, k, n) for k in range(m)]
+        claim = cref.product_sum(fid, tabs, n)
+        ref = cref.prove(fid, tabs, n, d, claim, False)
+        for threads in (1, 3, 8):
+            got = cref.prove(fid, tabs, n, d, claim, False, fast=True, threads=threads)
+            assert all((x == y).all() for x, y in zip(ref, got)), (fid, n, m, d, threads)
