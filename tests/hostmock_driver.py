@@ -149,6 +149,24 @@ def main():
     except zk.ZkError as e:
         check(e.status == 7, ("sop verify: wrong sum status", e.status))
 
+    # random term structures (1..8 terms of 1..8 factors over 1..8 tables, repeated factors, any MAX_VAR_DEGREE 1..4):
+    # the library (api.cu + the real kernel source) against the reference-shaped C oracle
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        fid = int(rng.integers(0, 2))
+        nt = int(rng.integers(1, 9))
+        terms = [[int(x) for x in rng.integers(0, nt, size=int(rng.integers(1, 9)))] for _ in range(int(rng.integers(1, 9)))]
+        n, d = int(rng.integers(1, 6)), int(rng.integers(1, 5))
+        refs = [cref.gen_table(fid, 1000 + trial, 20 + k, n) for k in range(nt)]
+        rsum = cref.sop_sum(fid, refs, terms, n)
+        rp, ch, fin = cref.prove_sop(fid, refs, terms, n, d, rsum)
+        sp = zk.SumOfProductsPoly.new([zk.MultiLinearPolynomial.new(n, r, field=fid, ctx=ctx) for r in refs], terms)
+        check((sp.sum_mont() == rsum).all(), ("fuzz sop sum", trial, terms))
+        prover = zk.SumcheckProver(d)
+        proof, gch = prover.prove_partial(sp, zk.from_mont(fid, rsum)[0])
+        check((proof._round_polys_mont == rp).all() and gch == cref.mont_to_ints(fid, ch) and prover.final_evals == cref.mont_to_ints(fid, fin),
+              ("fuzz sop prove", trial, fid, n, d, terms))
+
     # ---- NTT: single-GPU entry (buffer swap with the plan), then the multi-GPU step functions with virtual ranks
     for fid in (0, 1):
         for n in (0, 1, 4, 7, 9):

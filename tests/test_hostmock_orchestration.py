@@ -53,7 +53,7 @@ def test_api_orchestration_against_the_oracle_under_the_host_mock():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "hostmock_driver.py")], capture_output=True, text=True, env=env, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     res = json.loads(r.stdout.strip().splitlines()[-1])
-    assert res["hostmock_orchestration_ok"] and res["checks"] >= 229 and not res["failures"], res
+    assert res["hostmock_orchestration_ok"] and res["checks"] >= 300 and not res["failures"], res
 
 
 def test_sharded_entry_points_with_ranks_as_threads_under_the_host_mock():

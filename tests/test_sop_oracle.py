@@ -121,6 +121,26 @@ def test_python_and_c_oracles_agree_and_verifier_accepts(cref, shape):
     assert (ch2 != cch).any()
 
 
+def test_python_and_c_oracles_agree_on_random_term_structures(cref):
+    rng = np.random.default_rng(7)
+    for trial in range(25):
+        fid = int(rng.integers(0, 2))
+        F = O.FIELDS[fid]
+        nt = int(rng.integers(1, 7))
+        terms = [[int(x) for x in rng.integers(0, nt, size=int(rng.integers(1, 6)))] for _ in range(int(rng.integers(1, 7)))]
+        n, d = int(rng.integers(1, 5)), int(rng.integers(1, 5))
+        ints = [O.gen_table(F, 500 + trial, 20 + k, n) for k in range(nt)]
+        sp = O.SumOfProductsPoly([O.MultiLinearPolynomial(F, n, t) for t in ints], terms)
+        claim = sum(sp.prod_reduce()) % F.p
+        proof, ch = O.SumcheckProver(d).prove_partial(sp, claim)
+        tabs = [cref.ints_to_mont(fid, t) for t in ints]
+        csum = cref.sop_sum(fid, tabs, terms, n)
+        assert cref.mont_to_ints(fid, csum.reshape(1, 4))[0] == claim, (trial, terms)
+        rp, cch, _ = cref.prove_sop(fid, tabs, terms, n, d, csum)
+        assert cref.mont_to_ints(fid, rp.reshape(-1, 4)) == [x for r in proof.round_polys for x in r], (trial, terms, d)
+        assert cref.mont_to_ints(fid, cch) == ch
+
+
 def test_c_oracle_single_term_equals_reference_shaped_product_prover(cref):
     for fid, n, m, d in [(0, 5, 3, 3), (1, 4, 2, 2)]:
         tabs = [cref.gen_table(fid, 11, k, n) for k in range(m)]
