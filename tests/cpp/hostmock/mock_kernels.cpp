@@ -28,7 +28,7 @@ namespace {
 thread_local const host::Field* g_field = nullptr;
 thread_local host::El g_challenge;
 thread_local std::vector<host::El> g_sums;
-alignas(32) thread_local uint4 sop_smem[2 * 2 * kMaxFactors * 128];
+alignas(32) thread_local uint4 sop_smem[2 * 2 * kMaxFactors * 128 + 5 * (4 * 128 + 128 / 4)];  // e/d arrays + wide accumulators (D <= 4)
 constexpr int kThreads = 128;
 
 inline host::El el(const Fe& a) { host::El e; std::memcpy(e.v, a.v, 32); return e; }
@@ -173,7 +173,22 @@ cudaError_t sop_replay(int field, const TablePtrs& tabs, const SopSpec& spec, ui
     g_sums.assign((size_t)D + 1, F.zero());
     const unsigned grid = 3;
     const int skip1 = (fold && claim) ? 1 : 0;
-    if (fold) replay(grid, kThreads, [&] { sop_round_kernel<FT, D, true, false, false>(tabs, spec, q, FixedMul{}, FixedMulF64Sel{}, ReduceArgs{skip1}); });
+    const char* wide_env = std::getenv("ZK_B200_SOP_WIDE");  // the same knob the product launcher reads
+    if (wide_env && wide_env[0] == '1') {
+        // the deferred-reduction variant: block by block, shared memory cleared first (the kernel's accw_zero +
+        // __syncthreads(), which a thread-by-thread replay cannot interleave)
+        for (unsigned b = 0; b < grid; b++) {
+            std::memset(sop_smem, 0, sizeof(sop_smem));
+            gridDim = dim3(grid, 1, 1);
+            blockDim = dim3(kThreads, 1, 1);
+            for (unsigned t = 0; t < (unsigned)kThreads; t++) {
+                blockIdx = uint3{b, 0, 0};
+                threadIdx = uint3{t, 0, 0};
+                if (fold) sop_round_kernel<FT, D, true, false, true>(tabs, spec, q, FixedMul{}, FixedMulF64Sel{}, ReduceArgs{skip1});
+                else sop_round_kernel<FT, D, false, false, true>(tabs, spec, q, FixedMul{}, FixedMulF64Sel{}, ReduceArgs{0});
+            }
+        }
+    } else if (fold) replay(grid, kThreads, [&] { sop_round_kernel<FT, D, true, false, false>(tabs, spec, q, FixedMul{}, FixedMulF64Sel{}, ReduceArgs{skip1}); });
     else replay(grid, kThreads, [&] { sop_round_kernel<FT, D, false, false, false>(tabs, spec, q, FixedMul{}, FixedMulF64Sel{}, ReduceArgs{0}); });
     if (skip1) g_sums[1] = F.sub(el(*claim), g_sums[0]);
     publish(s, g_sums);
