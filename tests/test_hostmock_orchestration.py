@@ -112,6 +112,51 @@ def test_cpp_mirror_runs_under_the_host_mock():
         assert r.returncode == 0 and want in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_abi_walk_under_address_leak_and_ub_sanitizers():
+    """api.cu + the host mock + the replayed kernel sources built with -fsanitize=address,undefined, then a walk over the C
+    ABI (tests/cpp/test_abi_sanitized.cpp) and the two C++ mirror programs with leak detection on: "device" memory is
+    host memory under the mock, so an out-of-bounds access of the orchestration or of a replayed kernel, a double free,
+    or a leaked handle / event / buffer fails here.  (This run found the two CUDA events absorb_tables used to leak per
+    prove()/verify() call.)"""
+    import pytest
+
+    probe = subprocess.run(["g++", "-fsanitize=address,undefined", "-x", "c++", "-", "-o", os.devnull], input="int main(){return 0;}",
+                           capture_output=True, text=True)
+    if probe.returncode != 0:
+        pytest.skip("no sanitizer runtime in this toolchain")
+    out_dir = os.path.join(ROOT, "build", "asan")
+    os.makedirs(out_dir, exist_ok=True)
+    src = os.path.join(ROOT, "zk_b200", "csrc")
+    mock = os.path.join(ROOT, "tests", "cpp", "hostmock")
+    san = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g"]
+    common = ["g++", "-std=c++17", "-O1", "-w", "-fPIC", "-I", "/usr/local/cuda/include", "-I", src] + san
+    jobs = [
+        common + ["-x", "c++", "-fvisibility=hidden", "-c", os.path.join(src, "api.cu"), "-o", os.path.join(out_dir, "api.o")],
+        common + ["-fvisibility=hidden", "-c", os.path.join(mock, "mock_kernels.cpp"), "-o", os.path.join(out_dir, "mock_kernels.o")],
+        common + ["-c", os.path.join(mock, "mock_cudart.cpp"), "-o", os.path.join(out_dir, "mock_cudart.o")],
+        ["g++", "-std=c++17", "-O3", "-mavx512f", "-mavx512vl", "-fPIC", "-fvisibility=hidden", "-c", os.path.join(src, "keccak_avx512.cpp"),
+         "-o", os.path.join(out_dir, "keccak_avx512.o")],
+    ]
+    procs = [subprocess.Popen(j, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for j in jobs]
+    for p, j in zip(procs, jobs):
+        out, _ = p.communicate(timeout=900)
+        assert p.returncode == 0, " ".join(j) + "\n" + out[-3000:]
+    so = os.path.join(out_dir, "libzk_b200_hostmock.so")
+    r = subprocess.run(["g++", "-shared"] + san + ["-o", so] + [os.path.join(out_dir, f) for f in ("api.o", "mock_kernels.o", "mock_cudart.o", "keccak_avx512.o")]
+                       + ["-ldl", "-lpthread"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:halt_on_error=1", UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+    for srcfile, args, want in (("test_abi_sanitized.cpp", [], "ABI WALK OK"), ("test_reference_kats.cpp", [], "ALL C++ MIRROR TESTS PASSED"),
+                                ("test_sop_mirror_compiles.cpp", ["run"], "GKR LAYER OK")):
+        exe = os.path.join(out_dir, srcfile.replace(".cpp", "_asan"))
+        cmd = ["g++", "-std=c++17", "-O1"] + san + ["-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", srcfile), "-L", out_dir,
+                                                    "-lzk_b200_hostmock", f"-Wl,-rpath,{out_dir}", "-o", exe]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+        r = subprocess.run([exe] + args, capture_output=True, text=True, env=env, timeout=900)
+        assert r.returncode == 0 and want in r.stdout and "ERROR: " not in r.stderr, (srcfile, r.stdout[-1500:], r.stderr[-3000:])
+
+
 def test_the_host_mock_is_not_reachable_from_the_product():
     """Nothing under zk_b200/ (the product) or in the Makefile mentions the mock; only an explicit ZK_B200_LIB does."""
     for base, _, files in os.walk(os.path.join(ROOT, "zk_b200")):

@@ -699,7 +699,7 @@ int absorb_tables(zk_ctx* ctx, const zk_table* const* tables, unsigned m, zk::ho
     const uint64_t chunk = (uint64_t)1 << 20;  // 32 MiB per chunk, double buffered
     uint8_t* dbuf[2] = {nullptr, nullptr};
     uint8_t* hbuf[2] = {nullptr, nullptr};
-    cudaEvent_t done[2];
+    cudaEvent_t done[2] = {nullptr, nullptr};
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < 2 && e == cudaSuccess; i++) {
         e = cudaMalloc((void**)&dbuf[i], chunk * 32);
@@ -732,6 +732,7 @@ int absorb_tables(zk_ctx* ctx, const zk_table* const* tables, unsigned m, zk::ho
     for (int i = 0; i < 2; i++) {
         if (dbuf[i]) cudaFree(dbuf[i]);
         if (hbuf[i]) cudaFreeHost(hbuf[i]);
+        if (done[i]) cudaEventDestroy(done[i]);  // (found by the host-mock run under AddressSanitizer: two events leaked per call)
     }
     return st;
 }
