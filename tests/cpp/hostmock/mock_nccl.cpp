@@ -47,7 +47,8 @@ struct Comm {
 };
 
 std::mutex g_mu;
-std::map<std::string, Group*> g_groups;
+// never destroyed (the groups stay reachable until the process ends, so leak checkers do not count them)
+std::map<std::string, Group*>& g_groups = *new std::map<std::string, Group*>();
 uint64_t g_next_id = 1;
 thread_local Comm* t_open_comm = nullptr;  // the communicator the calling rank opened a group on
 

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "zk_b200.h"
@@ -15,7 +16,61 @@
         if (st__ != ZK_OK) { std::printf("%s -> %d (%s)\n", #call, st__, zk_status_string(st__)); return 1; } \
     } while (0)
 
-int main() {
+// One rank of a sharded job (ranks are threads; mock_nccl.cpp provides the collectives): sharded ProductPoly and
+// sum-of-products provers at two gather thresholds, the multi-GPU NTT forward and back, then everything released.
+static int sharded_rank(int rank, int world, const void* nccl_id) {
+    zk_ctx* ctx = nullptr;
+    CHECK(zk_ctx_create_sharded(0, rank, world, nccl_id, &ctx));
+    const unsigned n = 8, d = 3;
+    uint64_t sum[4], rp[8 * 4 * 4], ch[8 * 4], fin[4 * 4];
+    const uint8_t tl[3] = {2, 2, 3}, tf[7] = {0, 2, 0, 3, 1, 2, 3};
+    for (uint64_t thr : {(uint64_t)4096, (uint64_t)2}) {
+        CHECK(zk_ctx_set_gather_threshold(ctx, thr));
+        zk_table* t[4];
+        for (unsigned k = 0; k < 4; k++) CHECK(zk_table_generate(ctx, 0, 11, k, n, &t[k]));
+        CHECK(zk_product_sum(ctx, t, 3, sum));
+        CHECK(zk_sumcheck_prove(ctx, t, 3, d, sum, 0, rp, ch, fin));
+        for (unsigned k = 0; k < 4; k++) zk_table_free(t[k]);
+        for (unsigned k = 0; k < 4; k++) CHECK(zk_table_generate(ctx, 0, 11, k, n, &t[k]));
+        CHECK(zk_sop_sum(ctx, t, 4, tl, tf, 3, sum));
+        CHECK(zk_sumcheck_prove_sop(ctx, t, 4, tl, tf, 3, d, sum, 0, rp, ch, fin));
+        uint64_t sub[4], ch2[8 * 4];
+        CHECK(zk_sumcheck_verify_partial(0, sum, rp, n, d, sub, ch2));
+        for (unsigned k = 0; k < 4; k++) zk_table_free(t[k]);
+    }
+    for (int field = 0; field < 2; field++) {
+        zk_table* a = nullptr;
+        CHECK(zk_table_generate(ctx, field, 3, 1, n, &a));
+        std::vector<uint64_t> before(4u << n), after(4u << n);
+        CHECK(zk_table_download(ctx, a, before.data()));
+        CHECK(zk_ntt_sharded(ctx, a, 0));
+        CHECK(zk_ntt_sharded(ctx, a, 1));
+        CHECK(zk_table_download(ctx, a, after.data()));
+        const size_t local = ((size_t)4 << n) / (size_t)world;
+        if (std::memcmp(before.data(), after.data(), local * 8) != 0) { std::printf("sharded ntt round trip (rank %d)\n", rank); return 1; }
+        zk_table_free(a);
+    }
+    zk_ctx_destroy(ctx);
+    return 0;
+}
+
+static int sharded_jobs() {
+    for (int world : {2, 4}) {
+        unsigned char id[128];
+        CHECK(zk_nccl_unique_id(id));
+        std::vector<std::thread> th;
+        std::vector<int> rc((size_t)world, -1);
+        for (int r = 0; r < world; r++) th.emplace_back([&, r] { rc[(size_t)r] = sharded_rank(r, world, id); });
+        for (auto& t : th) t.join();
+        for (int r = 0; r < world; r++)
+            if (rc[(size_t)r] != 0) { std::printf("world %d rank %d failed\n", world, r); return 1; }
+    }
+    std::printf("SHARDED WALK OK\n");
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc > 1 && std::strcmp(argv[1], "sharded") == 0) return sharded_jobs();
     zk_ctx* ctx = nullptr;
     CHECK(zk_ctx_create(0, &ctx));
     for (int field = 0; field < 2; field++) {

@@ -145,12 +145,16 @@ def test_abi_walk_under_address_leak_and_ub_sanitizers():
     r = subprocess.run(["g++", "-shared"] + san + ["-o", so] + [os.path.join(out_dir, f) for f in ("api.o", "mock_kernels.o", "mock_cudart.o", "keccak_avx512.o")]
                        + ["-ldl", "-lpthread"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
-    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:halt_on_error=1", UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
-    for srcfile, args, want in (("test_abi_sanitized.cpp", [], "ABI WALK OK"), ("test_reference_kats.cpp", [], "ALL C++ MIRROR TESTS PASSED"),
-                                ("test_sop_mirror_compiles.cpp", ["run"], "GKR LAYER OK")):
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-fvisibility=hidden", "-shared"] + san + [os.path.join(mock, "mock_nccl.cpp"),
+                        "-o", os.path.join(out_dir, "libnccl.so.2"), "-lpthread"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:halt_on_error=1", UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1",
+               LD_LIBRARY_PATH=out_dir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    for srcfile, args, want in (("test_abi_sanitized.cpp", [], "ABI WALK OK"), ("test_abi_sanitized.cpp", ["sharded"], "SHARDED WALK OK"),
+                                ("test_reference_kats.cpp", [], "ALL C++ MIRROR TESTS PASSED"), ("test_sop_mirror_compiles.cpp", ["run"], "GKR LAYER OK")):
         exe = os.path.join(out_dir, srcfile.replace(".cpp", "_asan"))
         cmd = ["g++", "-std=c++17", "-O1"] + san + ["-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", srcfile), "-L", out_dir,
-                                                    "-lzk_b200_hostmock", f"-Wl,-rpath,{out_dir}", "-o", exe]
+                                                    "-lzk_b200_hostmock", f"-Wl,-rpath,{out_dir}", "-lpthread", "-o", exe]
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-3000:]
         r = subprocess.run([exe] + args, capture_output=True, text=True, env=env, timeout=900)
