@@ -159,9 +159,40 @@ int main(int argc, char** argv) {
         CHECK(zk_table_upload_local(ctx, field, raw.data(), 16, 4, &loc));
         zk_table_free(loc);
         for (unsigned k = 0; k < 4; k++) zk_table_free(t[k]);
-        // refused calls must not leak either
+        // refused calls must not leak (or touch anything out of bounds) either
         zk_table* bad = nullptr;
         if (zk_table_upload(ctx, field, raw.data(), 15, 4, &bad) != ZK_ERR_EVAL_LEN) { std::printf("expected ZK_ERR_EVAL_LEN\n"); return 1; }
+        {
+            zk_table *a = nullptr, *b = nullptr, *out = nullptr;
+            CHECK(zk_table_generate(ctx, field, 1, 0, 4, &a));
+            CHECK(zk_table_generate(ctx, field, 1, 1, 5, &b));
+            zk_table* mixed[2] = {a, b};
+            zk_table* twice[2] = {a, a};
+            uint64_t o[64], pt[5 * 4] = {0};
+            const uint8_t tl1[1] = {2}, tf1[2] = {0, 1}, tf_bad[2] = {0, 7};
+            int want[] = {
+                zk_product_sum(ctx, mixed, 2, o) == ZK_ERR_NVARS_MISMATCH,
+                zk_product_sum(ctx, mixed, 0, o) == ZK_ERR_EMPTY_PRODUCT,
+                zk_sumcheck_prove(ctx, mixed, 2, 2, o, 0, o, o, o) == ZK_ERR_NVARS_MISMATCH,
+                zk_mle_evaluate(ctx, a, pt, 3, o) == ZK_ERR_EVALUATE_ARITY,
+                zk_mle_partial_evaluate(ctx, a, 3, pt, 2, &out) == ZK_ERR_VAR_RANGE,
+                zk_product_round_poly(ctx, twice, 1, ZK_MAX_DEGREE + 1, o) == ZK_ERR_UNSUPPORTED,
+                zk_sop_round_poly(ctx, twice, 2, tl1, tf1, 1, 2, o) == ZK_ERR_INVALID_ARG,       /* a table listed twice */
+                zk_sop_round_poly(ctx, mixed, 1, tl1, tf_bad, 1, 2, o) == ZK_ERR_INVALID_ARG,    /* factor index out of range */
+                zk_sop_round_poly(ctx, mixed, 1, tl1, tf1, 1, 9, o) != ZK_OK,
+                zk_sumcheck_verify(ctx, mixed, 1, o, o, 3, 2) == ZK_ERR_PROOF_ROUNDS,
+                zk_ntt_virtual_sharded(ctx, a, 8, 0) == ZK_ERR_UNSUPPORTED,                        /* 16 points < 8^2 */
+                zk_ntt_virtual_sharded(ctx, a, 3, 0) == ZK_ERR_UNSUPPORTED,
+                zk_ntt_host(ctx, field, o, 12, 0) == ZK_ERR_NOT_POW2,
+                zk_table_upload_local(ctx, field, o, 3, 4, &out) == ZK_ERR_EVAL_LEN,
+                zk_sumcheck_prove_host(ctx, field, nullptr, 0, 4, 2, nullptr, 0, o, o, o, o) == ZK_ERR_EMPTY_PRODUCT,
+            };
+            for (size_t i = 0; i < sizeof(want) / sizeof(want[0]); i++)
+                if (!want[i]) { std::printf("refused call %zu returned an unexpected status\n", i); return 1; }
+            if (out != nullptr) { std::printf("a refused call produced a table\n"); return 1; }
+            zk_table_free(a);
+            zk_table_free(b);
+        }
     }
     zk_transcript* tr = zk_transcript_new();
     zk_transcript_append(tr, (const uint8_t*)"abc", 3);
