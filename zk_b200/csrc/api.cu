@@ -43,11 +43,8 @@ struct NcclApi {
 };
 constexpr int kNcclUint8 = 1, kNcclUint64 = 5, kNcclSum = 0;
 
-NcclApi& nccl() {
-    static NcclApi api;
-    static bool tried = false;
-    if (tried) return api;
-    tried = true;
+NcclApi load_nccl() {
+    NcclApi api;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
         api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
@@ -66,6 +63,10 @@ NcclApi& nccl() {
     api.GroupStart = (int (*)())dlsym(api.handle, "ncclGroupStart");
     api.GroupEnd = (int (*)())dlsym(api.handle, "ncclGroupEnd");
     api.p2p_ok = api.ok && api.Send && api.Recv && api.GroupStart && api.GroupEnd;
+    return api;
+}
+NcclApi& nccl() {  // resolved once, thread-safely (contexts of one process may be created from different threads)
+    static NcclApi api = load_nccl();
     return api;
 }
 }  // namespace
@@ -738,13 +739,12 @@ int absorb_tables(zk_ctx* ctx, const zk_table* const* tables, unsigned m, zk::ho
 }
 
 // Env-gated per-phase log in the spirit of the reference's `stat` crate (stat/src/lib.rs:12-30, PERF_LOG=true).
-bool perf_log_enabled() {
-    static int v = -1;
-    if (v < 0) {
+bool perf_log_enabled() {  // a magic static: contexts may live on different threads (one thread per zk_ctx)
+    static const bool on = [] {
         const char* e = std::getenv("PERF_LOG");
-        v = (e && std::strcmp(e, "true") == 0) ? 1 : 0;
-    }
-    return v == 1;
+        return e && std::strcmp(e, "true") == 0;
+    }();
+    return on;
 }
 
 // Value at x of the polynomial of degree < np given by its evaluations ys[t] at t = 0..np-1 (barycentric form, no
