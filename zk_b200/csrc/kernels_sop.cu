@@ -16,6 +16,7 @@
 // Rounds >= 1 derive S(1) from the previous round polynomial (one evaluation point less to multiply out) when
 // MAX_VAR_DEGREE covers the longest term; FP64 folds are wired behind ZK_B200_SOP_FOLD_PIPE.  No deferred
 // reduction or dynamic chunks yet (kernels_sumcheck.cu has those).
+#include <atomic>
 #include <cstdlib>
 
 #include "kernels.h"
@@ -37,12 +38,13 @@ cudaError_t do_sop_v(const TablePtrs& tabs, const SopSpec& spec, uint64_t q, con
                                                          (int)sop_smem_total(kMaxFactors, D + 1, WIDE));
     if (attr != cudaSuccess) return attr;
     const size_t smem = sop_smem_total(spec.n_tables, D + 1, WIDE);
-    static int bpsm_cache[kMaxFactors + 1] = {0};
-    int& bpsm = bpsm_cache[spec.n_tables];
+    static std::atomic<int> bpsm_cache[kMaxFactors + 1];  // zero-initialised; filled on first use per table count
+    int bpsm = bpsm_cache[spec.n_tables].load(std::memory_order_relaxed);
     if (bpsm == 0) {
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sop_round_kernel<F, D, FOLD, F64, WIDE>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
         bpsm = nb;
+        bpsm_cache[spec.n_tables].store(nb, std::memory_order_relaxed);
     }
     const unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
     const FixedMul tab = (FOLD && !F64) ? make_fixed<F>(r) : FixedMul{};
