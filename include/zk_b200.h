@@ -77,6 +77,8 @@ ZK_API int zk_ctx_create(int device, zk_ctx** out);
  * rank 0 and distributed by the launcher (torch.distributed / MPI / a file). */
 ZK_API int zk_nccl_unique_id(void* id_out_128);
 ZK_API int zk_ctx_create_sharded(int device, int rank, int world, const void* nccl_id, zk_ctx** out);
+/* Releases the context's streams, scratch, plans and communicator.  Tables created on it must be freed FIRST
+ * (zk_table_free reads its context to select the device). */
 ZK_API void zk_ctx_destroy(zk_ctx* ctx);
 ZK_API int zk_ctx_rank(const zk_ctx* ctx);
 ZK_API int zk_ctx_world(const zk_ctx* ctx);
