@@ -20,7 +20,18 @@ import sys
 from conftest import ROOT
 
 
+_HOSTMOCK_SO = None
+
+
 def _build_hostmock():
+    """Builds build/libzk_b200_hostmock.so (+ build/mock/libnccl.so.2) once per test session."""
+    global _HOSTMOCK_SO
+    if _HOSTMOCK_SO is None:
+        _HOSTMOCK_SO = _build_hostmock_once()
+    return _HOSTMOCK_SO
+
+
+def _build_hostmock_once():
     out_dir = os.path.join(ROOT, "build", "mock")
     os.makedirs(out_dir, exist_ok=True)
     src = os.path.join(ROOT, "zk_b200", "csrc")
