@@ -707,7 +707,6 @@ int absorb_tables(zk_ctx* ctx, const zk_table* const* tables, unsigned m, zk::ho
         if (e == cudaSuccess) e = cudaHostAlloc((void**)&hbuf[i], chunk * 32, cudaHostAllocDefault);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
     }
-    struct Job { uint64_t n; };
     int st = ZK_OK;
     if (e == cudaSuccess) {
         // pipeline: while the host hashes chunk c, the device produces chunk c+1
@@ -829,7 +828,6 @@ static int prove_core(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
     zk::TablePtrs cur = ptrs_of(tables, m);
     uint64_t cur_len = tables[0]->local_len;
     bool sharded = ctx->world > 1;
-    auto cleanup = [&]() {};
 
     // Gather the per-rank residual tables (local length L) into full tables of L*world entries on every rank.
     auto gather = [&]() -> int {
@@ -882,16 +880,16 @@ static int prove_core(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
     if (n > 0) {
         if (sharded && (cur_len < 2 || cur_len <= ctx->gather_threshold)) {
             st = gather();
-            if (st != ZK_OK) { cleanup(); return st; }
+            if (st != ZK_OK) return st;
         }
         cudaError_t e = timed([&] { next_seq(ctx, sharded); return launch_sums(); });
-        if (e != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "round_poly"); }
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "round_poly");
         if (perf_log_enabled()) {
             cudaStreamSynchronize(ctx->stream);
             std::fprintf(stderr, "[zk_b200 rank %d] round 0 kernel done at %.3f ms\n", ctx->rank, timer.ms());
         }
         st = finish_reduction(ctx, field, np, S.data(), sharded);
-        if (st != ZK_OK) { cleanup(); return st; }
+        if (st != ZK_OK) return st;
         if (perf_log_enabled()) std::fprintf(stderr, "[zk_b200 rank %d] round 0 reduced at %.3f ms\n", ctx->rank, timer.ms());
     }
     El r = F.zero();
@@ -917,9 +915,9 @@ static int prove_core(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
                 cur_len /= 2;
                 return ee;
             });
-            if (e != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "fold"); }
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "fold");
             st = gather();
-            if (st != ZK_OK) { cleanup(); return st; }
+            if (st != ZK_OK) return st;
             e = timed([&] { next_seq(ctx, sharded); return launch_sums(); });
         } else {
             // S_{round+1}(0) + S_{round+1}(1) = S_round(r): the kernel skips the t = 1 term and derives it (sharded:
@@ -943,18 +941,18 @@ static int prove_core(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
             e = timed([&] { next_seq(ctx, sharded); return launch_fold_sums(rf, claim_ptr); });
             cur_len /= 2;
         }
-        if (e != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "fold_round_poly"); }
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "fold_round_poly");
         st = finish_reduction(ctx, field, np, S.data(), sharded);
-        if (st != ZK_OK) { cleanup(); return st; }
+        if (st != ZK_OK) return st;
     }
     // last fold (prover.rs:64 in the final iteration): 2 -> 1 entries per factor
     if (n > 0) {
         if (sharded) {  // only reachable when world > 1 and the table never got small enough: gather now
             st = gather();
-            if (st != ZK_OK) { cleanup(); return st; }
+            if (st != ZK_OK) return st;
         }
         cudaError_t e = zk::launch_fold(field, cur, (int)m, cur_len / 2, fe_from_u64x4(r.v), ctx->stream, &ctx->launches);
-        if (e != cudaSuccess) { cleanup(); return cuda_fail(ctx, e, "final fold"); }
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "final fold");
         cur_len /= 2;
     }
     if (final_evals_out) {
@@ -969,7 +967,6 @@ static int prove_core(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
             ctx->prove_ms[2] += ms;
         }
     }
-    cleanup();
     count(ctx);
     ctx->prove_ms[0] = timer.ms();
     return ZK_OK;
