@@ -39,6 +39,8 @@ def _build_hostmock_once():
     common = ["g++", "-std=c++17", "-O2", "-w", "-fPIC", "-I", "/usr/local/cuda/include", "-I", src]
     jobs = [
         (common + ["-x", "c++", "-fvisibility=hidden", "-c", os.path.join(src, "api.cu"), "-o", os.path.join(out_dir, "api.o")]),
+        (common + ["-x", "c++", "-fvisibility=hidden", "-c", os.path.join(src, "api_sumcheck.cu"), "-o", os.path.join(out_dir, "api_sumcheck.o")]),
+        (common + ["-x", "c++", "-fvisibility=hidden", "-c", os.path.join(src, "api_ntt.cu"), "-o", os.path.join(out_dir, "api_ntt.o")]),
         (common + ["-fvisibility=hidden", "-c", os.path.join(mock, "mock_kernels.cpp"), "-o", os.path.join(out_dir, "mock_kernels.o")]),
         (common + ["-c", os.path.join(mock, "mock_cudart.cpp"), "-o", os.path.join(out_dir, "mock_cudart.o")]),
         (["g++", "-std=c++17", "-O3", "-mavx512f", "-mavx512vl", "-fPIC", "-fvisibility=hidden", "-c", os.path.join(src, "keccak_avx512.cpp"),
@@ -52,7 +54,7 @@ def _build_hostmock_once():
                         "-o", os.path.join(out_dir, "libnccl.so.2"), "-lpthread"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     so = os.path.join(ROOT, "build", "libzk_b200_hostmock.so")
-    r = subprocess.run(["g++", "-shared", "-o", so] + [os.path.join(out_dir, f) for f in ("api.o", "mock_kernels.o", "mock_cudart.o", "keccak_avx512.o")]
+    r = subprocess.run(["g++", "-shared", "-o", so] + [os.path.join(out_dir, f) for f in ("api.o", "api_sumcheck.o", "api_ntt.o", "mock_kernels.o", "mock_cudart.o", "keccak_avx512.o")]
                        + ["-ldl", "-lpthread"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return so
@@ -145,6 +147,8 @@ def test_abi_walk_under_address_leak_and_ub_sanitizers():
     common = ["g++", "-std=c++17", "-O1", "-w", "-fPIC", "-I", "/usr/local/cuda/include", "-I", src] + san
     jobs = [
         common + ["-x", "c++", "-fvisibility=hidden", "-c", os.path.join(src, "api.cu"), "-o", os.path.join(out_dir, "api.o")],
+        common + ["-x", "c++", "-fvisibility=hidden", "-c", os.path.join(src, "api_sumcheck.cu"), "-o", os.path.join(out_dir, "api_sumcheck.o")],
+        common + ["-x", "c++", "-fvisibility=hidden", "-c", os.path.join(src, "api_ntt.cu"), "-o", os.path.join(out_dir, "api_ntt.o")],
         common + ["-fvisibility=hidden", "-c", os.path.join(mock, "mock_kernels.cpp"), "-o", os.path.join(out_dir, "mock_kernels.o")],
         common + ["-c", os.path.join(mock, "mock_cudart.cpp"), "-o", os.path.join(out_dir, "mock_cudart.o")],
         ["g++", "-std=c++17", "-O3", "-mavx512f", "-mavx512vl", "-fPIC", "-fvisibility=hidden", "-c", os.path.join(src, "keccak_avx512.cpp"),
@@ -155,7 +159,7 @@ def test_abi_walk_under_address_leak_and_ub_sanitizers():
         out, _ = p.communicate(timeout=900)
         assert p.returncode == 0, " ".join(j) + "\n" + out[-3000:]
     so = os.path.join(out_dir, "libzk_b200_hostmock.so")
-    r = subprocess.run(["g++", "-shared"] + san + ["-o", so] + [os.path.join(out_dir, f) for f in ("api.o", "mock_kernels.o", "mock_cudart.o", "keccak_avx512.o")]
+    r = subprocess.run(["g++", "-shared"] + san + ["-o", so] + [os.path.join(out_dir, f) for f in ("api.o", "api_sumcheck.o", "api_ntt.o", "mock_kernels.o", "mock_cudart.o", "keccak_avx512.o")]
                        + ["-ldl", "-lpthread"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     r = subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-fvisibility=hidden", "-shared"] + san + [os.path.join(mock, "mock_nccl.cpp"),

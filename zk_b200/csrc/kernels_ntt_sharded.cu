@@ -1,5 +1,5 @@
 // kernels_ntt_sharded.cu — launchers of the multi-GPU NTT's own kernels (ntt_sharded_kernels.cuh); the transform of
-// each rank's shard is the single-GPU NTT of kernels_ntt.cu, the exchanges are NCCL send/recv groups (api.cu).
+// each rank's shard is the single-GPU NTT of kernels_ntt.cu, the exchanges are NCCL send/recv groups (api_ntt.cu).
 #include "kernels.h"
 #include "ntt_sharded_kernels.cuh"
 
