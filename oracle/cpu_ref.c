@@ -412,16 +412,14 @@ static void mt_run(void *(*fn)(void *), mt_job *jobs, int n_jobs) {
     fn(&jobs[0]);
     for (int i = 1; i < n_jobs; i++) pthread_join(th[i], NULL);
 }
-EXPORT int zko_prove_fast_mt(int field, uint64_t *const *tables, unsigned m, unsigned n_vars, unsigned degree,
-                             const uint64_t sum[4], uint64_t *round_polys_out, uint64_t *challenges_out,
-                             uint64_t *finals_out, int n_threads) {
-    const field_t *F = &FIELDS[field];
-    if (m > 8 || degree > 15 || n_threads < 1 || n_threads > 64) return -1;
-    keccak_t tr; k_init(&tr);
-    uint8_t be[32]; fe s; memcpy(s.v, sum, 32); f_to_be32(&s, be, F); k_update(&tr, be, 32);
-    unsigned nv = n_vars;
+/* rounds first_round .. n_vars-1 of the streamlined prover on tables of 2^(n_vars-first_round) entries, continuing
+ * the transcript `tr` */
+static void mt_rounds(const field_t *F, keccak_t *tr, uint64_t *const *tables, unsigned m, unsigned n_vars, unsigned first_round,
+                      unsigned degree, uint64_t *round_polys_out, uint64_t *challenges_out, int n_threads) {
+    uint8_t be[32];
+    unsigned nv = n_vars - first_round;
     mt_job jobs[64];
-    for (unsigned round = 0; round < n_vars; round++) {
+    for (unsigned round = first_round; round < n_vars; round++) {
         const long half = (long)1 << (nv - 1);
         const int nj = half >= 4096 ? n_threads : 1;   /* small rounds: thread start-up would dominate */
         for (int i = 0; i < nj; i++) {
@@ -434,15 +432,104 @@ EXPORT int zko_prove_fast_mt(int field, uint64_t *const *tables, unsigned m, uns
             acc[t] = f_zero();
             for (int i = 0; i < nj; i++) acc[t] = f_add(&acc[t], &jobs[i].loc[t], F);
             memcpy(round_polys_out + 4 * ((size_t)round * (degree + 1) + t), acc[t].v, 32);
-            f_to_be32(&acc[t], be, F); k_update(&tr, be, 32);
+            f_to_be32(&acc[t], be, F); k_update(tr, be, 32);
         }
-        fe r = t_sample(&tr, F);
+        fe r = t_sample(tr, F);
         memcpy(challenges_out + 4 * (size_t)round, r.v, 32);
         for (int i = 0; i < nj; i++) jobs[i].r = r;
         mt_run(mt_fold_worker, jobs, nj);
         nv--;
     }
+}
+EXPORT int zko_prove_fast_mt(int field, uint64_t *const *tables, unsigned m, unsigned n_vars, unsigned degree,
+                             const uint64_t sum[4], uint64_t *round_polys_out, uint64_t *challenges_out,
+                             uint64_t *finals_out, int n_threads) {
+    const field_t *F = &FIELDS[field];
+    if (m > 8 || degree > 15 || n_threads < 1 || n_threads > 64) return -1;
+    keccak_t tr; k_init(&tr);
+    uint8_t be[32]; fe s; memcpy(s.v, sum, 32); f_to_be32(&s, be, F); k_update(&tr, be, 32);
+    mt_rounds(F, &tr, tables, m, n_vars, 0, degree, round_polys_out, challenges_out, n_threads);
     if (finals_out) for (unsigned k = 0; k < m; k++) memcpy(finals_out + 4 * k, tables[k], 32);
+    return 0;
+}
+
+/* The same proof for the SEEDED synthetic tables (zko_gen_table, table ids 0..m-1) at sizes whose tables do not fit the
+ * host: round 0 streams the generator (no table is ever materialised at 2^n_vars entries), the fold at the first
+ * challenge regenerates every pair and writes the 2^(n_vars-1)-entry tables, the remaining rounds are mt_rounds.
+ * The claimed sum is the true sum S_0(0) + S_0(1) (returned in claim_out) — exactly what
+ * `prove_partial(poly, poly.sum())` absorbs (prover.rs:42).  Used offline by tests/golden/make_fullsize_digests.py for
+ * 2^27 .. 2^30 entries; the CPU suite checks it against zko_prove at small sizes. */
+typedef struct {
+    const field_t *F; int field; uint64_t seed; unsigned m, degree, n_vars; long half, lo, hi; fe r; fe loc[16]; fe **out;
+} gen_job;
+static void gen_pair(const gen_job *J, unsigned k, long j, fe *lo, fe *hi) {
+    zko_gen_table(J->field, J->seed, k, J->n_vars, (uint64_t)j, 1, 1, lo->v);
+    zko_gen_table(J->field, J->seed, k, J->n_vars, (uint64_t)(j + J->half), 1, 1, hi->v);
+}
+static void *gen_sum_worker(void *arg) {
+    gen_job *J = (gen_job *)arg; const field_t *F = J->F;
+    for (unsigned t = 0; t <= J->degree; t++) J->loc[t] = f_zero();
+    for (long j = J->lo; j < J->hi; j++) {
+        fe e[8], d[8], hi;
+        for (unsigned k = 0; k < J->m; k++) { gen_pair(J, k, j, &e[k], &hi); d[k] = f_sub(&hi, &e[k], F); }
+        for (unsigned t = 0; t <= J->degree; t++) {
+            fe pr = e[0];
+            for (unsigned k = 1; k < J->m; k++) pr = f_mul(&pr, &e[k], F);
+            J->loc[t] = f_add(&J->loc[t], &pr, F);
+            for (unsigned k = 0; k < J->m; k++) e[k] = f_add(&e[k], &d[k], F);
+        }
+    }
+    return NULL;
+}
+static void *gen_fold_worker(void *arg) {
+    gen_job *J = (gen_job *)arg; const field_t *F = J->F;
+    for (unsigned k = 0; k < J->m; k++)
+        for (long j = J->lo; j < J->hi; j++) {
+            fe lo, hi; gen_pair(J, k, j, &lo, &hi);
+            fe d = f_sub(&lo, &hi, F); fe x = f_mul(&J->r, &d, F); J->out[k][j] = f_sub(&lo, &x, F);   /* evaluation_form.rs:68 */
+        }
+    return NULL;
+}
+static void gen_run(void *(*fn)(void *), gen_job *jobs, int n_jobs) {
+    pthread_t th[64];
+    for (int i = 1; i < n_jobs; i++) pthread_create(&th[i], NULL, fn, &jobs[i]);
+    fn(&jobs[0]);
+    for (int i = 1; i < n_jobs; i++) pthread_join(th[i], NULL);
+}
+EXPORT int zko_prove_generated_mt(int field, uint64_t seed, unsigned m, unsigned n_vars, unsigned degree, uint64_t claim_out[4],
+                                  uint64_t *round_polys_out, uint64_t *challenges_out, uint64_t *finals_out, int n_threads) {
+    const field_t *F = &FIELDS[field];
+    if (m > 8 || degree > 15 || degree < 1 || n_threads < 1 || n_threads > 64 || n_vars < 1) return -1;
+    const long half = (long)1 << (n_vars - 1);
+    gen_job jobs[64];
+    const int nj = half >= 64 ? n_threads : 1;
+    fe *tabs[8];
+    for (unsigned k = 0; k < m; k++) { tabs[k] = (fe *)malloc((size_t)half * sizeof(fe)); if (!tabs[k]) return -2; }
+    for (int i = 0; i < nj; i++) {
+        jobs[i].F = F; jobs[i].field = field; jobs[i].seed = seed; jobs[i].m = m; jobs[i].degree = degree; jobs[i].n_vars = n_vars;
+        jobs[i].half = half; jobs[i].lo = half * i / nj; jobs[i].hi = half * (i + 1) / nj; jobs[i].out = tabs;
+    }
+    gen_run(gen_sum_worker, jobs, nj);
+    fe acc[16];
+    for (unsigned t = 0; t <= degree; t++) {
+        acc[t] = f_zero();
+        for (int i = 0; i < nj; i++) acc[t] = f_add(&acc[t], &jobs[i].loc[t], F);
+    }
+    keccak_t tr; k_init(&tr);
+    uint8_t be[32];
+    fe claim = f_add(&acc[0], &acc[1], F);                              /* the true sum: sum over the last variable first */
+    memcpy(claim_out, claim.v, 32);
+    f_to_be32(&claim, be, F); k_update(&tr, be, 32);                    /* prover.rs:42 */
+    for (unsigned t = 0; t <= degree; t++) {
+        memcpy(round_polys_out + 4 * (size_t)t, acc[t].v, 32);
+        f_to_be32(&acc[t], be, F); k_update(&tr, be, 32);
+    }
+    fe r = t_sample(&tr, F);
+    memcpy(challenges_out, r.v, 32);
+    for (int i = 0; i < nj; i++) jobs[i].r = r;
+    gen_run(gen_fold_worker, jobs, nj);
+    mt_rounds(F, &tr, (uint64_t *const *)tabs, m, n_vars, 1, degree, round_polys_out, challenges_out, n_threads);
+    for (unsigned k = 0; k < m; k++) { if (finals_out) memcpy(finals_out + 4 * k, tabs[k], 32); free(tabs[k]); }
     return 0;
 }
 

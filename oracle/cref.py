@@ -34,6 +34,7 @@ def lib():
         _lib.zko_prove.restype = C.c_int
         _lib.zko_prove_fast.restype = C.c_int
         _lib.zko_prove_fast_mt.restype = C.c_int
+        _lib.zko_prove_generated_mt.restype = C.c_int
         _lib.zko_prove_sop.restype = C.c_int
         _lib.zko_sop_sum.restype = C.c_int
         _lib.zko_verify_internal.restype = C.c_int
@@ -134,6 +135,18 @@ def prove(field: int, tables, n_vars: int, degree: int, sum_mont: np.ndarray, ab
                              _p(fin))
     assert rc == 0
     return rp, ch, fin
+
+
+def prove_generated(field: int, seed: int, m: int, n_vars: int, degree: int, threads: int = 1):
+    """prove_partial of the seeded generator tables 0..m-1 (claim = their true sum) without materialising them at full
+    size (zko_prove_generated_mt).  Returns (claim (4,), round_polys, challenges, finals)."""
+    claim = np.zeros(4, dtype=np.uint64)
+    rp = np.zeros((n_vars, degree + 1, 4), dtype=np.uint64)
+    ch = np.zeros((n_vars, 4), dtype=np.uint64)
+    fin = np.zeros((m, 4), dtype=np.uint64)
+    rc = lib().zko_prove_generated_mt(field, C.c_uint64(seed), m, n_vars, degree, _p(claim), _p(rp), _p(ch), _p(fin), int(threads))
+    assert rc == 0, rc
+    return claim, rp, ch, fin
 
 
 def _terms_flat(terms):

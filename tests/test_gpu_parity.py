@@ -304,3 +304,9 @@ def test_config2_bit_exact_vs_cpu_2p20_shape(zk, ctx, cref):
     proof = prover.prove(pp.clone(), cref.mont_to_ints(0, claim.reshape(1, 4))[0])
     assert (proof._round_polys_mont == rp).all()
     assert zk.SumcheckVerifier.verify(pp, proof) is True
+
+
+def test_upload_local_round_trip(zk, ctx, cref):
+    """zk_table_upload_local: a shard uploaded as it is comes back unchanged."""
+    loc = cref.gen_table(0, 2, 2, 9)
+    assert (zk.MultiLinearPolynomial.new_local(9, loc).evaluation_slice_mont() == loc).all()

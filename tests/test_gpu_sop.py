@@ -144,3 +144,16 @@ def test_zero_variables_and_argument_errors(zk, ctx):
     u = zk.MultiLinearPolynomial.generate(5, 0)
     with pytest.raises(zk.ZkError, match="don't share the same number of variables"):
         zk.SumOfProductsPoly.new([t[0], u], [[0, 1]])
+
+
+def test_prove_and_verify_with_the_initial_absorb(zk, ctx):
+    """prove (tables absorbed first) <-> SumcheckVerifier.verify over the sum of products (zk_sumcheck_verify_sop):
+    accept, Ok(false) is unreachable without breaking a round check first, the reference's Err strings."""
+    sp = gpu_sop(zk, 0, 11, 9, 4, GKR_TERMS)
+    keep = sp.clone()
+    proof = zk.SumcheckProver(3).prove(sp, keep.sum())
+    assert zk.SumcheckVerifier.verify(keep, proof) is True
+    with pytest.raises(zk.ZkError, match="require 1 round poly for each variable"):
+        zk.SumcheckVerifier.verify(keep, zk.SumcheckProof.from_values(0, proof.sum, proof.round_polys[:-1]))
+    with pytest.raises(zk.ZkError, match="claimed_sum != p\\(0\\) \\+ p\\(1\\)"):
+        zk.SumcheckVerifier.verify(keep, zk.SumcheckProof.from_values(0, proof.sum + 1, proof.round_polys))

@@ -337,3 +337,16 @@ def test_multithreaded_streamlined_prover_is_bit_identical(cref):
         for threads in (1, 3, 8):
             got = cref.prove(fid, tabs, n, d, claim, False, fast=True, threads=threads)
             assert all((x == y).all() for x, y in zip(ref, got)), (fid, n, m, d, threads)
+
+
+def test_streaming_generated_prover_is_bit_identical(cref):
+    """oracle/cpu_ref.c::zko_prove_generated_mt (the offline oracle behind the 2^27 .. 2^30 digests of
+    tests/golden/fullsize_digests.json: tables regenerated from the seed instead of held at full size): same claim and
+    proof as the reference-shaped prover on the materialised tables."""
+    for fid, n, m, d, threads in [(0, 13, 3, 3, 1), (0, 14, 3, 3, 5), (1, 12, 2, 2, 8), (0, 11, 1, 1, 2), (0, 1, 3, 3, 4), (0, 2, 2, 3, 1)]:
+        tabs = [cref.gen_table(fid, 0x5EED000000000001, k, n) for k in range(m)]
+        claim = cref.product_sum(fid, tabs, n)
+        ref = cref.prove(fid, tabs, n, d, claim, False)
+        gclaim, *got = cref.prove_generated(fid, 0x5EED000000000001, m, n, d, threads)
+        assert (gclaim == claim).all(), (fid, n, m, d)
+        assert all((x == y).all() for x, y in zip(ref, got)), (fid, n, m, d, threads)

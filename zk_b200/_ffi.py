@@ -82,7 +82,7 @@ SIGNATURES = {
     "zk_transcript_append": (None, [vp, C.c_char_p, C.c_size_t]),
     "zk_transcript_sample_field_element": (C.c_int, [vp, C.c_int, vp]),
     "zk_transcript_sample_n_field_elements": (C.c_int, [vp, C.c_int, C.c_uint, vp]),
-    "zk_keccak256": (None, [C.c_char_p, C.c_size_t, vp]),
+    "zk_keccak256": (None, [vp, C.c_size_t, vp]),
     "zk_ntt": (C.c_int, [vp, vp, C.c_int]),
     "zk_ntt_host": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_int]),
     "zk_ntt_sharded": (C.c_int, [vp, vp, C.c_int]),
