@@ -141,7 +141,11 @@ ZK_API int zk_product_prod_reduce(zk_ctx* ctx, const zk_table* const* tables, un
 ZK_API int zk_product_sum(zk_ctx* ctx, const zk_table* const* tables, unsigned m, uint64_t out[4]);
 /* One round polynomial: evaluations at t = 0..degree of sum_x prod_k A_k(t, x)   (sumcheck/src/prover.rs:48-56). */
 ZK_API int zk_product_round_poly(zk_ctx* ctx, const zk_table* const* tables, unsigned m, unsigned degree, uint64_t* out);
-/* poly = poly.partial_evaluate(0, &[r]) in place (prover.rs:64): every table halves. */
+/* poly = poly.partial_evaluate(0, &[r]) in place (prover.rs:64): every table halves.  The in-place entry points (this
+ * one, zk_product_fold_then_round_poly, zk_sumcheck_prove*) need DISTINCT tables: the same handle or device buffer listed
+ * twice is ZK_ERR_INVALID_ARG — the reference's ProductPoly owns its factors (`vec![f.clone(), f.clone()]` are two
+ * vectors), so pass a zk_table_clone for f * f (the Python / C++ / Rust mirrors do).  The read-only calls above accept
+ * repeated handles. */
 ZK_API int zk_product_fold_inplace(zk_ctx* ctx, zk_table* const* tables, unsigned m, const uint64_t r[4]);
 /* The fused step: fold at r, then the next round polynomial, in one pass over the tables. */
 ZK_API int zk_product_fold_then_round_poly(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned degree,
@@ -150,7 +154,7 @@ ZK_API int zk_product_fold_then_round_poly(zk_ctx* ctx, zk_table* const* tables,
 /* ---- sumcheck  (sumcheck/src/prover.rs, verifier.rs, lib.rs) -------------------------------------- */
 /* SumcheckProver::<degree,F>::prove (absorb_initial_poly != 0, prover.rs:15-20) or ::prove_partial
  * (== 0, prover.rs:24-30).  CONSUMES the tables (the reference takes `poly` by value): on return their
- * contents are unspecified and they may only be freed.
+ * contents are unspecified and they may only be freed.  The tables must be distinct (see zk_product_fold_inplace).
  *   round_polys_out : n_vars * (degree+1) elements — SumcheckProof.round_polys (lib.rs:8-11)
  *   challenges_out  : n_vars elements (may be NULL)
  *   final_evals_out : m elements A_k(r_0..r_{n-1}) (may be NULL) */

@@ -157,6 +157,32 @@ def test_verify_partial_host_vs_golden(zk, golden):
         zk.SumcheckVerifier.verify_partial(bad)
 
 
+def test_verifier_rejects_non_canonical_proof_elements(zk, golden):
+    """The proof is untrusted: an element encoded as value + p (a second limb pattern of the same field element, which the
+    transcript would hash as the reduced value) must be refused, not accepted as a different-but-equal proof."""
+    from zk_b200 import _ffi
+
+    lib = _ffi.lib()
+    c = {x["name"]: x for x in golden["small_cases"]}["B2_prove_partial_2ab3bc_sum10"]
+    F = O.FIELDS[0]
+    n, np1 = len(c["round_polys"]), len(c["round_polys"][0])
+    claim = zk.to_mont(0, [hx(c["claim"])])
+    rp = zk.to_mont(0, [hx(x) for r in c["round_polys"] for x in r]).reshape(n, np1, 4)
+    sub, ch = np.zeros(4, dtype=np.uint64), np.zeros((n, 4), dtype=np.uint64)
+    assert lib.zk_sumcheck_verify_partial(0, claim.ctypes.data, rp.ctypes.data, n, np1 - 1, sub.ctypes.data, ch.ctypes.data) == 0
+
+    def plus_p(limbs):
+        v = sum(int(x) << (64 * i) for i, x in enumerate(limbs)) + F.p
+        assert v < 1 << 256
+        return np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+    bad = rp.copy()
+    bad[1, 0] = plus_p(rp[1, 0])
+    assert lib.zk_sumcheck_verify_partial(0, claim.ctypes.data, bad.ctypes.data, n, np1 - 1, sub.ctypes.data, ch.ctypes.data) == 12
+    bad_claim = plus_p(claim[0]).reshape(1, 4)
+    assert lib.zk_sumcheck_verify_partial(0, bad_claim.ctypes.data, rp.ctypes.data, n, np1 - 1, sub.ctypes.data, ch.ctypes.data) == 12
+
+
 def test_proof_dump_layout(zk, golden):
     """zk_sumcheck_proof_dump: BE32(sum) || rounds || challenges || finals, host only."""
     c = {x["name"]: x for x in golden["seeded_cases"]}["seeded_n4_m3_d3_partial"]

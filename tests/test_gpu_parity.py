@@ -310,3 +310,37 @@ def test_upload_local_round_trip(zk, ctx, cref):
     """zk_table_upload_local: a shard uploaded as it is comes back unchanged."""
     loc = cref.gen_table(0, 2, 2, 9)
     assert (zk.MultiLinearPolynomial.new_local(9, loc).evaluation_slice_mont() == loc).all()
+
+
+def test_square_of_one_polynomial_vs_oracle(zk, ctx, cref):
+    """ProductPoly::new(vec![f.clone(), f.clone(), g]) (the reference's factors are owned vectors): the mirror clones a handle
+    listed twice, the proof equals the oracle's on [f, f, g]; the raw C ABI refuses the same handle twice on the in-place
+    paths (the fused fold would fold that buffer once per listing)."""
+    from zk_b200 import _ffi
+
+    lib = _ffi.lib()
+    n, d, seed = 11, 3, 77
+    refs = [cref.gen_table(0, seed, 0, n), cref.gen_table(0, seed, 0, n), cref.gen_table(0, seed, 1, n)]
+    claim = cref.product_sum(0, refs, n)
+    rp, ch, fin = cref.prove(0, refs, n, d, claim, False)
+    f = zk.MultiLinearPolynomial.generate(n, 0, seed=seed)
+    g = zk.MultiLinearPolynomial.generate(n, 1, seed=seed)
+    pp = zk.ProductPoly.new([f, f, g])
+    assert (pp.sum_mont() == claim).all()
+    prover = zk.SumcheckProver(d)
+    proof, chs = prover.prove_partial(pp, cref.mont_to_ints(0, claim.reshape(1, 4))[0])
+    assert (proof._round_polys_mont == rp).all()
+    assert chs == cref.mont_to_ints(0, ch) and prover.final_evals == cref.mont_to_ints(0, fin)
+    # raw ABI: the same handle twice
+    f2 = zk.MultiLinearPolynomial.generate(n, 0, seed=seed)
+    arr = zk._table_array([f2, f2])
+    out = np.zeros((n, 3, 4), dtype=np.uint64)
+    assert lib.zk_sumcheck_prove(ctx.h, arr, 2, 2, claim.ctypes.data, 0, out.ctypes.data, None, None) == 12
+    r = zk.to_mont(0, [5])
+    assert lib.zk_product_fold_inplace(ctx.h, arr, 2, r.ctypes.data) == 12
+    assert lib.zk_product_fold_then_round_poly(ctx.h, arr, 2, 2, r.ctypes.data, out.ctypes.data) == 12
+    # read-only calls accept it: sum of f*f
+    s = np.zeros(4, dtype=np.uint64)
+    assert lib.zk_product_sum(ctx.h, arr, 2, s.ctypes.data) == 0
+    assert (s == cref.product_sum(0, refs[:2], n)).all()
+    assert (f2.evaluation_slice_mont() == refs[0]).all()  # untouched by the refused calls

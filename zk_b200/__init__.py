@@ -253,7 +253,14 @@ class ProductPoly:
     """P(x) = A(x).B(x).C(x)  (polynomial/src/product_poly.rs:4-10)."""
 
     def __init__(self, polynomials: Sequence[MultiLinearPolynomial], _checked: bool = False):
-        self.polynomials = list(polynomials)
+        # The reference's ProductPoly OWNS its factors (`ProductPoly::new(vec![f.clone(), f.clone()])` holds two
+        # vectors).  Here factors are handles to device tables, and the in-place folds of the prover need one buffer per
+        # factor: the same handle listed again is cloned, so ProductPoly.new([f, f]) is f * f like in the reference.
+        self.polynomials, seen = [], set()
+        for q in polynomials:
+            key = q._h.value if hasattr(q._h, "value") else q._h
+            self.polynomials.append(q.clone() if key in seen else q)
+            seen.add(key)
         self.ctx = self.polynomials[0].ctx if self.polynomials else Context.default()
 
     @classmethod

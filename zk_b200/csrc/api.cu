@@ -94,6 +94,16 @@ int product_check(zk_ctx* ctx, const zk_table* const* tables, unsigned m, bool d
     if (device_limits && m > ZK_MAX_FACTORS) return fail(ctx, ZK_ERR_UNSUPPORTED, "more than ZK_MAX_FACTORS factors");
     return ZK_OK;
 }
+// The in-place / consuming entry points fold every listed table once per launch: the same table (or the same device
+// buffer) listed twice would be folded twice.  The reference's ProductPoly owns its factors (`vec![f.clone(), f.clone()]`
+// are two buffers), so a caller that wants f * f passes a clone — the mirrors do that for it.
+int distinct_check(zk_ctx* ctx, const zk_table* const* tables, unsigned m) {
+    for (unsigned a = 0; a < m; a++)
+        for (unsigned b = a + 1; b < m; b++)
+            if (tables[a] == tables[b] || tables[a]->data == tables[b]->data)
+                return fail(ctx, ZK_ERR_INVALID_ARG, "the same table is listed twice: in-place folds need distinct tables (pass a clone)");
+    return ZK_OK;
+}
 zk::TablePtrs ptrs_of(const zk_table* const* tables, unsigned m) {
     zk::TablePtrs p{};
     for (unsigned k = 0; k < m && k < (unsigned)zk::kMaxFactors; k++) p.t[k] = tables[k]->data;
@@ -120,7 +130,12 @@ int finish_reduction(zk_ctx* ctx, int field, int count_elems, uint64_t* out, boo
         if ((spins & 0x3fff) == 0x3fff) {
             cudaError_t q = cudaStreamQuery(ctx->stream);
             if (q == cudaSuccess) {
-                if (*flag != want) CU(ctx, cudaStreamSynchronize(ctx->stream));
+                // the stream has drained: the flag store must be visible after a synchronisation, otherwise the
+                // launch never published (a failed or skipped reduction) and result_host holds stale sums
+                if (*flag != want) {
+                    CU(ctx, cudaStreamSynchronize(ctx->stream));
+                    if (*flag != want) return fail(ctx, ZK_ERR_CUDA, "the reducing launch finished without publishing its result");
+                }
                 break;
             }
             if (q != cudaErrorNotReady) return cuda_fail(ctx, q, "round kernel");
@@ -544,6 +559,7 @@ int zk_product_round_poly(zk_ctx* ctx, const zk_table* const* tables, unsigned m
 int zk_product_fold_inplace(zk_ctx* ctx, zk_table* const* tables, unsigned m, const uint64_t r[4]) {
     if (!ctx || !r) return fail(ctx, ZK_ERR_INVALID_ARG);
     int st = product_check(ctx, tables, m, true);
+    if (st == ZK_OK) st = distinct_check(ctx, tables, m);
     if (st != ZK_OK) return st;
     if (tables[0]->n_vars == 0 || tables[0]->local_len < 2) return fail(ctx, ZK_ERR_VAR_RANGE);
     CU(ctx, cudaSetDevice(ctx->device));
@@ -562,6 +578,7 @@ int zk_product_fold_then_round_poly(zk_ctx* ctx, zk_table* const* tables, unsign
                                     const uint64_t r[4], uint64_t* out) {
     if (!ctx || !r || !out) return fail(ctx, ZK_ERR_INVALID_ARG);
     int st = product_check(ctx, tables, m, true);
+    if (st == ZK_OK) st = distinct_check(ctx, tables, m);
     if (st != ZK_OK) return st;
     if (degree > ZK_MAX_DEGREE) return fail(ctx, ZK_ERR_UNSUPPORTED, "degree > ZK_MAX_DEGREE");
     if (tables[0]->n_vars < 2 || tables[0]->local_len < 4) return fail(ctx, ZK_ERR_VAR_RANGE);

@@ -130,6 +130,7 @@ inline bool valid_field(int f) { return f == ZK_BLS12_381_FR || f == ZK_BLS12_37
 
 int table_alloc(zk_ctx* ctx, int field, unsigned n_vars, uint64_t local_len, zk_table** out);
 int product_check(zk_ctx* ctx, const zk_table* const* tables, unsigned m, bool device_limits);
+int distinct_check(zk_ctx* ctx, const zk_table* const* tables, unsigned m);  // consuming / in-place paths
 zk::TablePtrs ptrs_of(const zk_table* const* tables, unsigned m);
 // After a reducing kernel: (sharded) all-reduce the `count` partial elements exactly, then wait for the result in
 // pinned host memory and copy it out.

@@ -120,6 +120,7 @@ static int prove_core(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
                       uint64_t* final_evals_out, const zk::SopSpec* sop) {
     if (!ctx || !sum) return fail(ctx, ZK_ERR_INVALID_ARG);
     int st = product_check(ctx, tables, m, true);
+    if (st == ZK_OK) st = distinct_check(ctx, tables, m);  // the prover consumes (folds in place) every listed table
     if (st != ZK_OK) return st;
     if (degree > ZK_MAX_DEGREE) return fail(ctx, ZK_ERR_UNSUPPORTED, "degree > ZK_MAX_DEGREE");
     const unsigned n = tables[0]->n_vars;
@@ -534,6 +535,12 @@ int verify_internal(const Field& F, zk::host::Transcript& tr, const uint64_t sum
                     unsigned n_rounds, unsigned degree, El* subclaim_sum, uint64_t* challenges_out) {
     const int np = (int)degree + 1;
     El claimed = el_from(sum);
+    // The proof is untrusted input: the reference's proof holds `F` values, which are canonical by construction.  A limb
+    // pattern >= p would be hashed as its reduced value but compared as raw limbs (a second encoding of the same
+    // element): rejected here instead.
+    if (!F.is_canonical(claimed)) return ZK_ERR_INVALID_ARG;
+    for (size_t i = 0; i < (size_t)n_rounds * np; i++)
+        if (!F.is_canonical(el_from(round_polys + 4 * i))) return ZK_ERR_INVALID_ARG;
     tr.append_element(F, claimed);  // :50
     std::vector<El> rp(np), coef(np);
     for (unsigned r = 0; r < n_rounds; r++) {

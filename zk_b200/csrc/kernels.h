@@ -6,9 +6,31 @@
 #include <cstddef>
 #include <cstdint>
 
+#include <atomic>
+
 #include "field.cuh"
 
 namespace zk {
+
+// Function attributes (the opt-in to more than 48 KB of dynamic shared memory) and occupancy are PER DEVICE, and one
+// process may hold contexts on several devices (zk_ctx_create(device)), each driven by its own thread: lazily computed
+// values are cached per device ordinal, in atomics.  `compute` returns a positive value (blocks per SM), or a negated
+// cudaError_t, which is not cached.
+constexpr int kMaxDevices = 64;
+struct PerDeviceCache {
+    std::atomic<int> v[kMaxDevices];
+};
+template <class Fn>
+inline int per_device(PerDeviceCache& c, Fn&& compute) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return compute();
+    int x = c.v[dev].load(std::memory_order_acquire);
+    if (x <= 0) {
+        x = compute();
+        if (x > 0) c.v[dev].store(x, std::memory_order_release);
+    }
+    return x;
+}
 
 constexpr int kMaxFactors = 8;   // ProductPoly factor count supported on the device
 constexpr int kMaxDegree = 15;   // MAX_VAR_DEGREE supported (round polynomial has kMaxDegree+1 evaluations)

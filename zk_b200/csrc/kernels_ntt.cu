@@ -199,13 +199,13 @@ cudaError_t execute(NttPlan* p, Fe* data, Fe** result, cudaStream_t st, int* lau
     const uint64_t n = (uint64_t)1 << k;
     // split the k stages into ceil(k/9) passes of (almost) equal size, every pass >= 2 stages when k >= 4
     const unsigned n_pass = (k + kMaxTileLog - 1) / kMaxTileLog;
-    static bool attr_set = false;
     const size_t max_smem = (size_t)(2 * ((1u << kMaxTileLog) * kTileB) + (1u << kMaxTileLog)) * sizeof(uint4);
-    if (!attr_set) {
+    static PerDeviceCache attr_cache;  // the shared-memory opt-in is per device
+    const int attr = per_device(attr_cache, [max_smem] {
         cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+        return e == cudaSuccess ? 1 : -(int)e;
+    });
+    if (attr <= 0) return (cudaError_t)(-attr);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -34,18 +34,17 @@ constexpr size_t sop_smem_total(int n_tables, int np, bool wide) { return sop_sm
 template <class F, int D, bool FOLD, bool F64, bool WIDE>
 cudaError_t do_sop_v(const TablePtrs& tabs, const SopSpec& spec, uint64_t q, const Fe& r, const ReduceScratch& s,
                      cudaStream_t st, const Fe* claim) {
-    static const cudaError_t attr = cudaFuncSetAttribute(sop_round_kernel<F, D, FOLD, F64, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         (int)sop_smem_total(kMaxFactors, D + 1, WIDE));
-    if (attr != cudaSuccess) return attr;
     const size_t smem = sop_smem_total(spec.n_tables, D + 1, WIDE);
-    static std::atomic<int> bpsm_cache[kMaxFactors + 1];  // zero-initialised; filled on first use per table count
-    int bpsm = bpsm_cache[spec.n_tables].load(std::memory_order_relaxed);
-    if (bpsm == 0) {
+    static PerDeviceCache cache[kMaxFactors + 1];  // per device and table count (the shared-memory footprint depends on it)
+    const int bpsm = per_device(cache[spec.n_tables], [smem] {
+        cudaError_t e = cudaFuncSetAttribute(sop_round_kernel<F, D, FOLD, F64, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sop_smem_total(kMaxFactors, D + 1, WIDE));
+        if (e != cudaSuccess) return -(int)e;
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sop_round_kernel<F, D, FOLD, F64, WIDE>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
-        bpsm = nb;
-        bpsm_cache[spec.n_tables].store(nb, std::memory_order_relaxed);
-    }
+        return nb;
+    });
+    if (bpsm <= 0) return (cudaError_t)(-bpsm);
     const unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
     const FixedMul tab = (FOLD && !F64) ? make_fixed<F>(r) : FixedMul{};
     const FixedMulF64Sel tab64 = F64 ? make_fixed_f64<F>(r) : FixedMulF64Sel{};

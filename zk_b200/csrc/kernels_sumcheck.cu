@@ -314,12 +314,15 @@ cudaError_t do_round_v(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, co
     const FixedMul tab = (FOLD && !F64) ? make_fixed<F>(r) : FixedMul{};
     const FixedMulF64Sel tab64 = F64 ? make_fixed_f64<F>(r) : FixedMulF64Sel{};
     constexpr size_t smem = accw_bytes(D + 1);
-    static int bpsm = [] {
-        cudaFuncSetAttribute(round_kernel<F, D, FOLD, TOOM, F64, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static PerDeviceCache cache;
+    const int bpsm = per_device(cache, [] {
+        cudaError_t e = cudaFuncSetAttribute(round_kernel<F, D, FOLD, TOOM, F64, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -(int)e;
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<F, D, FOLD, TOOM, F64, DYN>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
         return nb;
-    }();
+    });
+    if (bpsm <= 0) return (cudaError_t)(-bpsm);
     unsigned grid = grid_for(q, kThreads, s.num_sms, bpsm);
     ReduceArgs ra = make_ra(s, 0);
     if (FOLD && claim && D >= 1) {
@@ -353,7 +356,7 @@ template <class F>
 cudaError_t round_poly_dispatch(const TablePtrs& tabs, int m, int degree, uint64_t half, const ReduceScratch& s,
                                 cudaStream_t st, int* launches) {
     if (has_fused_path(m, degree)) { ++*launches; return do_round_deg<F, false>(tabs, m, degree, half, Fe{}, s, st); }
-    static int bpsm = blocks_per_sm(eval_at_kernel<F>, kThreads);
+    const int bpsm = blocks_per_sm(eval_at_kernel<F>, kThreads);
     unsigned grid = grid_for(half, kThreads, s.num_sms, bpsm);
     for (int t = 0; t <= degree; t++) {
         ReduceArgs ra = make_ra(s, t);
@@ -388,7 +391,7 @@ cudaError_t fold_round_poly_dispatch(const TablePtrs& tabs, int m, int degree, u
 template <class F>
 cudaError_t product_sum_dispatch(const TablePtrs& tabs, int m, uint64_t n, const ReduceScratch& s, cudaStream_t st,
                                  int* launches) {
-    static int bpsm = blocks_per_sm(product_sum_kernel<F>, kThreads);
+    const int bpsm = blocks_per_sm(product_sum_kernel<F>, kThreads);
     unsigned grid = grid_for(n, kThreads, s.num_sms, bpsm);
     product_sum_kernel<F><<<grid, kThreads, 0, st>>>(tabs, m, n, make_ra(s, 0));
     ++*launches;

@@ -4,6 +4,7 @@
 // Integer modular sums are order independent, so any reduction tree is bit-exact with the reference's sequential
 // `.sum()` (sumcheck/src/prover.rs:53-54).
 #pragma once
+#include <atomic>
 #include <cstring>
 
 #include "field_f64.cuh"
@@ -166,7 +167,7 @@ __device__ __forceinline__ void reduce_publish(Fe* acc, const ReduceArgs& ra) {
 // ---- launch helpers ----------------------------------------------------------------------------
 template <class K>
 int blocks_per_sm(K kernel, int threads) {
-    int n = 0;
+    int n = 0;  // a host-side query of a few microseconds: not cached (its callers are not on the round loop)
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1) n = 1;
     return n;
 }
