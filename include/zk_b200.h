@@ -82,6 +82,10 @@ ZK_API int zk_ctx_create_sharded(int device, int rank, int world, const void* nc
 ZK_API void zk_ctx_destroy(zk_ctx* ctx);
 ZK_API int zk_ctx_rank(const zk_ctx* ctx);
 ZK_API int zk_ctx_world(const zk_ctx* ctx);
+/* 1 when the sharded context all-reduces the round sums through peer-mapped mailboxes inside the reducing launch (CUDA IPC
+ * over NVLink; set up collectively at creation), 0 when it uses the NCCL all-reduce (IPC unavailable, ZK_B200_MAILBOX=0,
+ * or a single rank).  The results are bit-identical either way. */
+ZK_API int zk_ctx_uses_mailbox(const zk_ctx* ctx);
 /* Local table length at or below which a sharded prove gathers the residual tables to every rank and
  * finishes without further collectives (default 4096). */
 ZK_API int zk_ctx_set_gather_threshold(zk_ctx* ctx, uint64_t local_len);

@@ -31,6 +31,11 @@ cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { *p = mock_alloc(by
 cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
 cudaError_t cudaHostGetDevicePointer(void** dev, void* host, unsigned) { *dev = host; return cudaSuccess; }
 cudaError_t cudaMemset(void* p, int v, size_t n) { std::memset(p, v, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }
+// no CUDA IPC in the mock: sharded contexts agree on the NCCL all-reduce (the fallback path of api.cu's mailbox_setup)
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind, cudaStream_t) {
     if (n) std::memmove(dst, src, n);
     return cudaSuccess;

@@ -232,7 +232,7 @@ def test_rust_ffi_is_in_sync_with_the_header():
     declared = re.findall(r"ZK_API[^;(]*?\b(zk_\w+)\s*\(", re.sub(r"/\*.*?\*/", " ", header, flags=re.S))
     ffi = open(os.path.join(ROOT, "rust", "zk-b200-sys", "src", "ffi.rs")).read()
     rust = re.findall(r"pub fn (zk_\w+)\(", ffi)
-    assert rust == declared and len(set(rust)) == len(rust) == 69
+    assert rust == declared and len(set(rust)) == len(rust) == 70
 
 
 def test_rust_sources_are_well_formed_and_only_call_declared_entry_points():

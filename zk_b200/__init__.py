@@ -109,6 +109,10 @@ class Context:
         lib().zk_ctx_last_prove_ms(self.h, buf)
         return {"total_ms": buf[0], "absorb_ms": buf[1], "kernel_ms": buf[2]}
 
+    def uses_mailbox(self) -> bool:
+        """True when this sharded context all-reduces the round sums inside the reducing launch (peer mailboxes over NVLink)."""
+        return bool(lib().zk_ctx_uses_mailbox(self.h))
+
     def set_gather_threshold(self, n: int):
         self.check(lib().zk_ctx_set_gather_threshold(self.h, n))
 

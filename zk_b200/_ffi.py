@@ -38,6 +38,7 @@ SIGNATURES = {
     "zk_ctx_destroy": (None, [vp]),
     "zk_ctx_rank": (C.c_int, [vp]),
     "zk_ctx_world": (C.c_int, [vp]),
+    "zk_ctx_uses_mailbox": (C.c_int, [vp]),
     "zk_ctx_set_gather_threshold": (C.c_int, [vp, C.c_uint64]),
     "zk_ctx_launch_count": (C.c_uint64, [vp]),
     "zk_ctx_last_round_ms": (C.c_uint, [vp, C.POINTER(C.c_float), C.c_uint]),

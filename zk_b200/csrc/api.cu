@@ -82,6 +82,8 @@ int table_alloc(zk_ctx* ctx, int field, unsigned n_vars, uint64_t local_len, zk_
     return ZK_OK;
 }
 
+void mailbox_teardown(zk_ctx* c);
+
 int product_check(zk_ctx* ctx, const zk_table* const* tables, unsigned m, bool device_limits) {
     if (m == 0 || tables == nullptr) return fail(ctx, ZK_ERR_EMPTY_PRODUCT);
     for (unsigned k = 0; k < m; k++)
@@ -113,8 +115,8 @@ zk::TablePtrs ptrs_of(const zk_table* const* tables, unsigned m) {
 // After a reducing kernel: (sharded) all-reduce the `count` partial elements exactly, then wait for the
 // result in pinned host memory and copy it out.
 int finish_reduction(zk_ctx* ctx, int field, int count_elems, uint64_t* out, bool allreduce) {
-    if (allreduce && ctx->world > 1) {
-        // the reducing launch already wrote one 32-bit limb per u64 lane (ReduceScratch::lanes)
+    if (allreduce && ctx->world > 1 && !ctx->mbox_in_flight) {
+        // NCCL fallback (no peer mailboxes): the reducing launch wrote one 32-bit limb per u64 lane (ReduceScratch::lanes)
         int rc = nccl().AllReduce(ctx->lanes, ctx->lanes, (size_t)count_elems * 8, kNcclUint64, kNcclSum, ctx->comm,
                                   ctx->stream);
         if (rc != 0) return fail(ctx, ZK_ERR_NCCL, nccl().GetErrorString ? nccl().GetErrorString(rc) : "allreduce");
@@ -127,6 +129,7 @@ int finish_reduction(zk_ctx* ctx, int field, int count_elems, uint64_t* out, boo
     volatile unsigned* flag = ctx->scratch.flag_host;
     const unsigned want = ctx->cur_seq;
     for (unsigned spins = 0; *flag != want; spins++) {
+        if (*flag == 0xffffffffu) return fail(ctx, ZK_ERR_NCCL, "a peer rank never delivered its round sums (mailbox timeout)");
         if ((spins & 0x3fff) == 0x3fff) {
             cudaError_t q = cudaStreamQuery(ctx->stream);
             if (q == cudaSuccess) {
@@ -144,6 +147,59 @@ int finish_reduction(zk_ctx* ctx, int field, int count_elems, uint64_t* out, boo
     std::atomic_thread_fence(std::memory_order_acquire);
     if (out) std::memcpy(out, ctx->scratch.result_host, (size_t)count_elems * 32);
     return ZK_OK;
+}
+
+// Peer mailboxes of a sharded context (kernels.h: MailboxArgs): allocate mine, exchange CUDA IPC handles over the NCCL
+// communicator, map every peer's.  Collective; every rank ends with the same answer (all ranks mapped everything, or
+// nobody uses the mailboxes and the NCCL all-reduce stays).  ZK_B200_MAILBOX=0 keeps NCCL (A/B runs).
+int mailbox_setup(zk_ctx* c) {
+    const char* env = std::getenv("ZK_B200_MAILBOX");
+    uint64_t ok = !(env && env[0] == '0') && c->world <= zk::kMaxRanks ? 1 : 0;
+    const size_t bytes = 2 * (size_t)zk::kMaxRanks * sizeof(zk::MailboxSlot);
+    unsigned char* hsend = nullptr;
+    unsigned char* hall = nullptr;
+    cudaIpcMemHandle_t mine_h;
+    std::memset(&mine_h, 0, sizeof(mine_h));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(c, cudaMalloc((void**)&hsend, 64));
+    CU(c, cudaMalloc((void**)&hall, 64 * (size_t)c->world));
+    if (cudaMalloc((void**)&c->mbox_mine, bytes) != cudaSuccess) { c->mbox_mine = nullptr; ok = 0; cudaGetLastError(); }
+    if (c->mbox_mine) {
+        CU(c, cudaMemsetAsync(c->mbox_mine, 0, bytes, c->stream));
+        if (ok && cudaIpcGetMemHandle(&mine_h, c->mbox_mine) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+    }
+    CU(c, cudaMemcpyAsync(hsend, &mine_h, 64, cudaMemcpyHostToDevice, c->stream));
+    if (nccl().AllGather(hsend, hall, 64, kNcclUint8, c->comm, c->stream) != 0) return fail(c, ZK_ERR_NCCL, "allgather(ipc handles)");
+    std::vector<cudaIpcMemHandle_t> all((size_t)c->world);
+    CU(c, cudaMemcpyAsync(all.data(), hall, 64 * (size_t)c->world, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int q = 0; q < c->world && ok; q++) {
+        if (q == c->rank) { c->mbox_peer[q] = c->mbox_mine; continue; }
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[(size_t)q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+        c->mbox_peer[q] = (zk::MailboxSlot*)p;
+    }
+    // agreement (and the barrier that orders every rank's memset before anyone's first store): sum of the ok flags
+    CU(c, cudaMemcpyAsync(c->lanes, &ok, 8, cudaMemcpyHostToDevice, c->stream));
+    if (nccl().AllReduce(c->lanes, c->lanes, 1, kNcclUint64, kNcclSum, c->comm, c->stream) != 0) return fail(c, ZK_ERR_NCCL, "allreduce(mailbox agreement)");
+    uint64_t sum = 0;
+    CU(c, cudaMemcpyAsync(&sum, c->lanes, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(hsend);
+    cudaFree(hall);
+    c->mbox_ready = (sum == (uint64_t)c->world);
+    if (!c->mbox_ready) mailbox_teardown(c);
+    return ZK_OK;
+}
+void mailbox_teardown(zk_ctx* c) {
+    for (int q = 0; q < zk::kMaxRanks; q++) {
+        if (c->mbox_peer[q] && q != c->rank) cudaIpcCloseMemHandle(c->mbox_peer[q]);
+        c->mbox_peer[q] = nullptr;
+    }
+    if (c->mbox_mine) cudaFree(c->mbox_mine);
+    c->mbox_mine = nullptr;
+    c->mbox_ready = false;
+    cudaGetLastError();
 }
 
 int ctx_init(zk_ctx* c) {
@@ -234,14 +290,23 @@ int zk_ctx_create_sharded(int device, int rank, int world, const void* nccl_id, 
             *out = nullptr;
             return ZK_ERR_NCCL;
         }
+        st = mailbox_setup(c);
+        if (st != ZK_OK) {
+            std::fprintf(stderr, "zk_ctx_create_sharded: %s\n", c->last_error.c_str());
+            zk_ctx_destroy(c);
+            *out = nullptr;
+            return st;
+        }
     }
     return ZK_OK;
 }
+int zk_ctx_uses_mailbox(const zk_ctx* c) { return c && c->mbox_ready ? 1 : 0; }
 
 void zk_ctx_destroy(zk_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    mailbox_teardown(c);
     if (c->comm) nccl().CommDestroy(c->comm);
     for (auto* pl : c->ntt_plans) zk::ntt_plan_destroy(pl);
     cudaFree(c->gather_buf);
@@ -548,7 +613,7 @@ int zk_product_round_poly(zk_ctx* ctx, const zk_table* const* tables, unsigned m
     if (degree > ZK_MAX_DEGREE) return fail(ctx, ZK_ERR_UNSUPPORTED, "degree > ZK_MAX_DEGREE");
     if (tables[0]->n_vars == 0 || tables[0]->local_len < 2) return fail(ctx, ZK_ERR_VAR_RANGE);
     CU(ctx, cudaSetDevice(ctx->device));
-    next_seq(ctx, true);
+    next_seq(ctx, true, zk::has_fused_path((int)m, (int)degree));
     CU(ctx, zk::launch_round_poly(tables[0]->field, ptrs_of(tables, m), (int)m, (int)degree, tables[0]->local_len / 2,
                                   ctx->scratch, ctx->stream, &ctx->launches));
     st = finish_reduction(ctx, tables[0]->field, (int)degree + 1, out, true);
@@ -583,7 +648,7 @@ int zk_product_fold_then_round_poly(zk_ctx* ctx, zk_table* const* tables, unsign
     if (degree > ZK_MAX_DEGREE) return fail(ctx, ZK_ERR_UNSUPPORTED, "degree > ZK_MAX_DEGREE");
     if (tables[0]->n_vars < 2 || tables[0]->local_len < 4) return fail(ctx, ZK_ERR_VAR_RANGE);
     CU(ctx, cudaSetDevice(ctx->device));
-    next_seq(ctx, true);
+    next_seq(ctx, true, zk::has_fused_path((int)m, (int)degree));
     CU(ctx, zk::launch_fold_round_poly(tables[0]->field, ptrs_of(tables, m), (int)m, (int)degree, tables[0]->local_len,
                                        fe_from_u64x4(r), ctx->scratch, ctx->stream, &ctx->launches));
     st = finish_reduction(ctx, tables[0]->field, (int)degree + 1, out, true);

@@ -53,6 +53,12 @@ struct zk_ctx {
     zk::ReduceScratch scratch{};
     zkapi::NcclComm comm = nullptr;
     uint64_t* lanes = nullptr;  // (kMaxDegree+1)*8 u64 lanes for the exact all-reduce
+    // the all-reduce fused into the reducing launch: peer-mapped mailboxes (kernels.h: MailboxArgs); NCCL stays the fallback
+    zk::MailboxSlot* mbox_mine = nullptr;
+    zk::MailboxSlot* mbox_peer[zk::kMaxRanks] = {};
+    bool mbox_ready = false;
+    bool mbox_in_flight = false;  // the reduction in flight all-reduces itself (no NCCL call, no narrowing launch)
+    unsigned mbox_seq = 0;
     uint64_t gather_threshold = 4096;
     std::string last_error;
     int launches = 0;
@@ -101,11 +107,25 @@ int cuda_fail(zk_ctx* ctx, cudaError_t e, const char* where);
 // every reducing launch publishes a fresh non-zero sequence number to the mapped completion flag
 // `will_allreduce`: the launch's result is a per-rank partial — it widens it into the all-reduce lanes and
 // leaves the flag alone; the narrowing kernel after the all-reduce publishes the sequence number instead.
-inline void next_seq(zk_ctx* ctx, bool will_allreduce = false) {
-    if (++ctx->cur_seq == 0) ctx->cur_seq = 1;
+// `single_launch`: the reduction is ONE reducing launch (every fused path); then a sharded context with mailboxes lets
+// that launch all-reduce through them and publish the final result itself.
+inline void next_seq(zk_ctx* ctx, bool will_allreduce = false, bool single_launch = true) {
+    ++ctx->cur_seq;
+    if (ctx->cur_seq == 0 || ctx->cur_seq == 0xffffffffu) ctx->cur_seq = 1;  // 0 = "do not publish", ~0 = mailbox timeout
     const bool sharded = will_allreduce && ctx->world > 1;
-    ctx->scratch.seq = sharded ? 0u : ctx->cur_seq;
-    ctx->scratch.lanes = sharded ? ctx->lanes : nullptr;
+    const bool mbox = sharded && ctx->mbox_ready && single_launch;
+    ctx->mbox_in_flight = mbox;
+    ctx->scratch.seq = (sharded && !mbox) ? 0u : ctx->cur_seq;
+    ctx->scratch.lanes = (sharded && !mbox) ? ctx->lanes : nullptr;
+    ctx->scratch.mbox.world = 0;
+    if (mbox) {
+        if (++ctx->mbox_seq == 0) ctx->mbox_seq = 1;  // every rank runs the same sequence of collective reductions
+        ctx->scratch.mbox.world = ctx->world;
+        ctx->scratch.mbox.rank = ctx->rank;
+        ctx->scratch.mbox.seq = ctx->mbox_seq;
+        ctx->scratch.mbox.mine = ctx->mbox_mine;
+        for (int q = 0; q < ctx->world; q++) ctx->scratch.mbox.peer[q] = ctx->mbox_peer[q];
+    }
 }
 inline void count(zk_ctx* ctx) {
     ctx->launches_total += (uint64_t)ctx->launches;

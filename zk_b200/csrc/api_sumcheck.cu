@@ -184,6 +184,8 @@ static int prove_core(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
                    : zk::launch_fold_round_poly(field, cur, (int)m, (int)degree, cur_len, rf, ctx->scratch, ctx->stream, &ctx->launches, claim_ptr);
     };
 
+    // one reducing launch per round (every fused path; the sum of products has no other): it may all-reduce in-kernel
+    const bool single_launch = sop != nullptr || zk::has_fused_path((int)m, (int)degree);
     std::vector<uint64_t> S((size_t)np * 4);
     const RoundPolyEvaluator round_eval(F, np);
     size_t ev = 0;
@@ -200,7 +202,7 @@ static int prove_core(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
             st = gather();
             if (st != ZK_OK) return st;
         }
-        cudaError_t e = timed([&] { next_seq(ctx, sharded); return launch_sums(); });
+        cudaError_t e = timed([&] { next_seq(ctx, sharded, single_launch); return launch_sums(); });
         if (e != cudaSuccess) return cuda_fail(ctx, e, "round_poly");
         if (perf_log_enabled()) {
             cudaStreamSynchronize(ctx->stream);
@@ -236,7 +238,7 @@ static int prove_core(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
             if (e != cudaSuccess) return cuda_fail(ctx, e, "fold");
             st = gather();
             if (st != ZK_OK) return st;
-            e = timed([&] { next_seq(ctx, sharded); return launch_sums(); });
+            e = timed([&] { next_seq(ctx, sharded, single_launch); return launch_sums(); });
         } else {
             // S_{round+1}(0) + S_{round+1}(1) = S_round(r): the kernel skips the t = 1 term and derives it (sharded:
             // the map is linear, so the value goes to rank 0 and zero to the others before the all-reduce).
@@ -256,7 +258,7 @@ static int prove_core(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
                 std::memcpy(claim_next.v, c.v, 32);
             }
             const Fe* claim_ptr = derive_s1 ? &claim_next : nullptr;
-            e = timed([&] { next_seq(ctx, sharded); return launch_fold_sums(rf, claim_ptr); });
+            e = timed([&] { next_seq(ctx, sharded, single_launch); return launch_fold_sums(rf, claim_ptr); });
             cur_len /= 2;
         }
         if (e != cudaSuccess) return cuda_fail(ctx, e, "fold_round_poly");

@@ -40,6 +40,27 @@ struct TablePtrs {
     Fe* t[kMaxFactors];
 };
 
+// ---- the round-sum all-reduce fused into the reducing launch (sharded contexts) ------------------------
+// Every rank owns a small mailbox in its HBM; the other ranks map it through CUDA IPC.  The last block of a reducing
+// launch stores its D+1 partial sums straight into slot [parity][own rank] of EVERY rank's mailbox over NVLink (peer
+// stores), then a sequence flag; it waits for the flags of all senders in its own mailbox, adds the partials in rank
+// order (exact modular sums, the same order on every rank: bit-identical results everywhere) and publishes like a
+// single-GPU launch.  No collective call and no second launch per round.  world == 0: not in use (single GPU, or the
+// NCCL fallback when IPC is unavailable).
+constexpr int kMaxRanks = 8;
+struct MailboxSlot {
+    Fe v[16];            // kMaxDegree + 1 partial sums
+    unsigned flag;       // sequence number of the round these partials belong to (written last)
+    unsigned pad[7];
+};
+struct MailboxArgs {
+    int world;                       // 0 = disabled
+    int rank;
+    unsigned seq;                    // this exchange's sequence number (> 0, the same on every rank)
+    MailboxSlot* mine;               // [2][kMaxRanks] slots in this GPU's memory
+    MailboxSlot* peer[kMaxRanks];    // the same array of every rank (peer[rank] == mine), peer-mapped
+};
+
 // Per-context scratch used by the reducing kernels.
 struct ReduceScratch {
     Fe* block_partials;      // [kMaxGridBlocks * (kMaxDegree+1)] device
@@ -52,6 +73,7 @@ struct ReduceScratch {
     unsigned seq;            // value the next reducing launch publishes (0 = do not publish)
     uint64_t* lanes;         // when non-null the reducing launch also widens its result into u64 lanes (sharded all-reduce input)
     int num_sms;
+    MailboxArgs mbox;        // world > 1: the launch all-reduces its result through the peer mailboxes itself
 };
 
 // ---- sumcheck hot path (kernels_sumcheck.cu) ---------------------------------------------------

@@ -351,6 +351,155 @@ cudaError_t do_round_deg(const TablePtrs& tabs, int m, int degree, uint64_t q, c
     }
 }
 
+// ---- the latency kernel of the small rounds --------------------------------------------------------------------
+// From about 2^17 items down a round no longer fills the GPU: with one item per thread its duration is the latency of ONE
+// item (six folds and seven products back to back, about 3400 dependent-ish instructions = 9 us) plus the wide-accumulator
+// and grid reductions, 23 - 27 us per launch whatever the size — eighteen such rounds are 6 % of a 2^26 proof.  Here EIGHT
+// lanes share an item: lanes 0 .. 2m-1 each fold one pair of one factor (lane 2k: (j, j+2q) -> lo_k, lane 2k+1:
+// (j+q, j+3q) -> hi_k, written back in place like the streaming kernel), the folded values travel by warp shuffle, and lane
+// t <= D multiplies its own evaluation point e_k(t) = lo_k + t (hi_k - lo_k) through the factors: the critical path is one
+// fold and m-1 products.  Plain reduced products (no wide accumulators to drain), a shuffle + shared-memory reduction of one
+// element per lane, the last block publishes exactly like reduce_publish.  Same field elements as the streaming kernel
+// (any exact evaluation of prover.rs:49-56 / :64 is), so which kernel a round takes is invisible in the proof.
+// m <= 4 (2m fold lanes) and D <= 4; other shapes stay on the streaming kernel.
+constexpr int kSmallGroup = 8;
+template <class F, int D>
+__global__ void __launch_bounds__(kThreads) round_small_kernel(TablePtrs tabs, int m, uint64_t q, Fe r_in, ReduceArgs ra) {
+    constexpr int NP = D + 1;
+    __shared__ Fe sh[kWarps][kSmallGroup];
+    __shared__ Fe sh_fin[kThreads / kSmallGroup][kSmallGroup];
+    __shared__ unsigned s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane & (kSmallGroup - 1), base = lane & ~(kSmallGroup - 1);
+    Fe r = r_in;  // a multiplier read from the constant bank makes ptxas split the wide multiplies: keep it in registers
+#pragma unroll
+    for (int i = 0; i < 8; i++) asm volatile("" : "+r"(r.v[i]));
+    const bool skip1 = ra.skip1 != 0;
+    const int k_mine = g >> 1, h_mine = g & 1;
+    const uint64_t items_per_grid = (uint64_t)gridDim.x * (kThreads / kSmallGroup);
+    Fe acc = fe_zero<F>();
+    // all lanes of a warp run the same number of iterations (the shuffles are warp-wide); `live` masks the ragged end
+#pragma unroll 1
+    for (uint64_t j0 = (uint64_t)blockIdx.x * (kThreads / kSmallGroup) + warp * (32 / kSmallGroup); j0 < q; j0 += items_per_grid) {
+        const uint64_t j = j0 + (lane >> 3);
+        const bool live = j < q;
+        Fe v = fe_zero<F>();
+        if (live && g < 2 * m) {
+            Fe* T = tabs.t[k_mine] + j + (h_mine ? q : 0);
+            const Fe a = ld_fe_stream(T), b = ld_fe_stream(T + 2 * q);
+            v = fe_fold<F>(a, b, r);  // a - r (a - b): evaluation_form.rs:68
+            st_fe(T, v);
+        }
+        Fe pr = fe_zero<F>();
+#pragma unroll 1
+        for (int k = 0; k < m; k++) {
+            Fe lo, hi;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                lo.v[i] = __shfl_sync(0xffffffffu, v.v[i], base + 2 * k);
+                hi.v[i] = __shfl_sync(0xffffffffu, v.v[i], base + 2 * k + 1);
+            }
+            // e = e_k(g): lo, hi, hi + d, hi + 2d, ...
+            Fe e = (g == 0) ? lo : hi;
+            if (D >= 2) {
+                const Fe d = fe_sub<F>(hi, lo);
+#pragma unroll
+                for (int t = 2; t <= D; t++) {
+                    const Fe e2 = fe_add<F>(e, d);
+                    if (g >= t) e = e2;
+                }
+            }
+            pr = (k == 0) ? e : fe_mul<F>(pr, e);
+        }
+        if (live && g < NP && !(skip1 && g == 1)) acc = fe_add<F>(acc, pr);
+    }
+    // warp: the four groups' lanes of the same point
+#pragma unroll
+    for (int off = kSmallGroup; off < 32; off <<= 1) {
+        Fe o;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o.v[i] = __shfl_xor_sync(0xffffffffu, acc.v[i], off);
+        acc = fe_add<F>(acc, o);
+    }
+    if (lane < kSmallGroup) sh[warp][lane] = acc;
+    __syncthreads();
+    if (gridDim.x == 1) {  // the last rounds of every proof: one block, nothing to hand over through global memory
+        if (threadIdx.x < kSmallGroup) {
+            Fe v = sh[0][threadIdx.x];
+#pragma unroll
+            for (int w = 1; w < kWarps; w++) v = fe_add<F>(v, sh[w][threadIdx.x]);
+            sh_fin[0][threadIdx.x] = v;
+        }
+        __syncthreads();
+        finish_last_block<F, NP, false>(&sh_fin[0][0], ra);
+        return;
+    }
+    if (threadIdx.x < NP) {
+        Fe v = sh[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < kWarps; w++) v = fe_add<F>(v, sh[w][threadIdx.x]);
+        st_fe(ra.block_partials + (size_t)blockIdx.x * NP + threadIdx.x, v);
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned tk = atomicAdd(ra.ticket, 1u);
+        s_last = (tk == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    {   // last block: thread (row, t) sums the partials of blocks row, row + 16, ... for point t
+        const int t = threadIdx.x & (kSmallGroup - 1), row = threadIdx.x >> 3;
+        Fe v = fe_zero<F>();
+        if (t < NP)
+            for (unsigned b = row; b < gridDim.x; b += kThreads / kSmallGroup) v = fe_add<F>(v, ld_fe_cg(ra.block_partials + (size_t)b * NP + t));
+        sh_fin[row][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kSmallGroup) {
+        Fe v = sh_fin[0][threadIdx.x];
+#pragma unroll 1
+        for (int row = 1; row < kThreads / kSmallGroup; row++) v = fe_add<F>(v, sh_fin[row][threadIdx.x]);
+        sh[0][threadIdx.x] = v;
+    }
+    __syncthreads();
+    finish_last_block<F, NP, false>(&sh[0][0], ra);
+}
+
+// Items at or below which the fused step takes the latency kernel (ZK_B200_SMALL_Q overrides; 0 disables it).
+inline uint64_t small_q_threshold() {
+    static const uint64_t v = [] {
+        const char* e = std::getenv("ZK_B200_SMALL_Q");
+        return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)1 << 13;  // measured crossover on B200: 2^13 items (profiles/r02_small_round_kernel_ab.txt)
+    }();
+    return v;
+}
+template <class F, int D>
+cudaError_t do_round_small_d(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st, const Fe* claim) {
+    const uint64_t per_block = kThreads / kSmallGroup;
+    uint64_t need = (q + per_block - 1) / per_block;
+    const uint64_t cap = (uint64_t)s.num_sms * 16 < (uint64_t)kMaxGridBlocks ? (uint64_t)s.num_sms * 16 : (uint64_t)kMaxGridBlocks;
+    if (need < 1) need = 1;
+    ReduceArgs ra = make_ra(s, 0);
+    if (claim) {
+        ra.skip1 = 1;
+        ra.claim = *claim;
+    }
+    round_small_kernel<F, D><<<(unsigned)(need < cap ? need : cap), kThreads, 0, st>>>(tabs, m, q, r, ra);
+    return cudaGetLastError();
+}
+template <class F>
+cudaError_t do_round_small(const TablePtrs& tabs, int m, int degree, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st,
+                           const Fe* claim) {
+    switch (degree) {
+        case 1: return do_round_small_d<F, 1>(tabs, m, q, r, s, st, claim);
+        case 2: return do_round_small_d<F, 2>(tabs, m, q, r, s, st, claim);
+        case 3: return do_round_small_d<F, 3>(tabs, m, q, r, s, st, claim);
+        case 4: return do_round_small_d<F, 4>(tabs, m, q, r, s, st, claim);
+        default: return cudaErrorInvalidValue;
+    }
+}
 
 template <class F>
 cudaError_t round_poly_dispatch(const TablePtrs& tabs, int m, int degree, uint64_t half, const ReduceScratch& s,
@@ -383,6 +532,10 @@ template <class F>
 cudaError_t fold_round_poly_dispatch(const TablePtrs& tabs, int m, int degree, uint64_t n_prev, const Fe& r,
                                      const ReduceScratch& s, cudaStream_t st, int* launches, const Fe* claim) {
     const uint64_t q = n_prev / 4;
+    if (has_fused_path(m, degree) && 2 * m <= kSmallGroup && q <= small_q_threshold()) {
+        ++*launches;
+        return do_round_small<F>(tabs, m, degree, q, r, s, st, claim);
+    }
     if (has_fused_path(m, degree)) { ++*launches; return do_round_deg<F, true>(tabs, m, degree, q, r, s, st, claim); }
     cudaError_t e = fold_dispatch<F>(tabs, m, n_prev / 2, r, &s, st, launches);
     if (e != cudaSuccess) return e;

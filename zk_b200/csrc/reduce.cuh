@@ -55,6 +55,7 @@ struct ReduceArgs {
     // publishes S(1) = claim - S(0): the same field element (prover.rs:49-56 computes it directly).
     int skip1;
     Fe claim;             // this rank's share of S_prev(r_prev): the value on rank 0, zero elsewhere (the map is linear)
+    MailboxArgs mbox;     // world > 1: all-reduce through the peer mailboxes inside this launch (kernels.h)
 };
 constexpr int kWorkCounterOffset = 32;  // the work counter lives 128 bytes after the ticket (own cache line)
 
@@ -93,6 +94,127 @@ __device__ __forceinline__ void toom_to_evals(Fe* v) {
     const Fe c1x3 = fe_add<F>(c1x2, c1), c2x9 = fe_add<F>(c2x8, c2);
     const Fe c3x27 = fe_sub<F>(fe_sub<F>(c3x32, c3x4), c3);
     v[3] = fe_add<F>(fe_add<F>(s0, c1x3), fe_add<F>(c2x9, c3x27));
+}
+
+// What ONE thread of the last block does with the NP grid-wide sums.  finalize: derive S(1) when the launch skipped it and
+// map the Toom point set back to t = 0..D (both maps are linear, so on a sharded run they are applied to the partial
+// sums before the exchange).  publish: device buffer, mapped host buffer, all-reduce lanes (NCCL fallback), re-arm the
+// ticket and the work counter, store the completion flag the host spins on.
+template <class F, int NP, bool TOOM = false>
+__device__ __forceinline__ void finalize_evals(Fe* fin, const ReduceArgs& ra) {
+    if (ra.skip1 && NP > 1) fin[1] = fe_sub<F>(ra.claim, fin[0]);
+    if (TOOM) toom_to_evals<F>(fin);
+}
+template <class F, int NP>
+__device__ __forceinline__ void publish_raw(const Fe* fin, const ReduceArgs& ra, unsigned seq_override = 0) {
+#pragma unroll
+    for (int t = 0; t < NP; t++) {
+        st_fe(ra.result_dev + ra.out_slot + t, fin[t]);
+        st_fe(ra.result_host + ra.out_slot + t, fin[t]);
+        if (ra.lanes) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) ra.lanes[(ra.out_slot + t) * 8 + i] = fin[t].v[i];
+        }
+    }
+    *ra.ticket = 0;  // ready for the next launch on this stream
+    ra.ticket[kWorkCounterOffset] = 0;
+    __threadfence_system();
+    const unsigned seq = seq_override ? seq_override : ra.seq;
+    if (seq != 0) {
+        *(volatile unsigned*)ra.flag_host = seq;
+        __threadfence_system();
+    }
+}
+template <class F, int NP, bool TOOM = false>
+__device__ __forceinline__ void publish_evals(Fe* fin, const ReduceArgs& ra) {
+    finalize_evals<F, NP, TOOM>(fin, ra);
+    publish_raw<F, NP>(fin, ra);
+}
+
+// ---- the all-reduce through the peer mailboxes (kernels.h: MailboxArgs), run by the whole last block ------------------
+constexpr unsigned kMailboxTimeoutFlag = 0xffffffffu;  // published instead of the sequence number when a peer never arrives
+__device__ __forceinline__ void st_fe_sys(Fe* p, const Fe& r) {  // peer (NVLink) store
+    asm volatile("st.global.v8.u32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]),
+                 "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7]), "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ Fe ld_fe_volatile(const Fe* p) {
+    Fe r;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]) : "l"(p) : "memory");
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(reinterpret_cast<const uint32_t*>(p) + 4)
+                 : "memory");
+    return r;
+}
+// s_fin[NP] (shared): in = this rank's partial sums, out = the sums over all ranks (identical on every rank).
+// s_in: shared scratch of kMaxRanks * NP elements.  Returns false (on every thread) if a peer did not arrive in time.
+template <class F, int NP>
+__device__ __forceinline__ bool mailbox_allreduce(Fe* s_fin, Fe* s_in, unsigned* s_ok, const MailboxArgs& mb) {
+    const unsigned par = mb.seq & 1u;
+    if (threadIdx.x == 0) *s_ok = 1u;
+    __syncthreads();
+    if ((int)threadIdx.x < mb.world) {
+        // thread q: my partials -> slot [par][my rank] of rank q's mailbox, then the flag
+        MailboxSlot* dst = mb.peer[threadIdx.x] + par * kMaxRanks + mb.rank;
+#pragma unroll 1
+        for (int t = 0; t < NP; t++) st_fe_sys(dst->v + t, s_fin[t]);
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&dst->flag), "r"(mb.seq) : "memory");
+        // thread q: wait for rank q's partials in my mailbox
+        const MailboxSlot* src = mb.mine + par * kMaxRanks + threadIdx.x;
+        unsigned f;
+        unsigned long long t0 = 0, now = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(&src->flag) : "memory");
+            if (f == mb.seq) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > 4000000000ull) {  // 4 s: a peer died or never launched — fail instead of hanging the GPU
+                *s_ok = 0u;
+                break;
+            }
+        }
+#pragma unroll 1
+        for (int t = 0; t < NP; t++) s_in[threadIdx.x * NP + t] = ld_fe_volatile(src->v + t);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < NP) {
+        Fe v = s_in[threadIdx.x];
+#pragma unroll 1
+        for (int q = 1; q < mb.world; q++) v = fe_add<F>(v, s_in[q * NP + threadIdx.x]);
+        s_fin[threadIdx.x] = v;
+    }
+    __syncthreads();
+    return *s_ok != 0u;
+}
+// Tail of every reducing kernel, run by the WHOLE last block once s_fin[NP] (shared) holds the grid-wide sums.
+template <class F, int NP, bool TOOM = false>
+__device__ __forceinline__ void finish_last_block(Fe* s_fin, const ReduceArgs& ra) {
+    __shared__ Fe s_in[kMaxRanks * NP];
+    __shared__ unsigned s_ok;
+    if (threadIdx.x == 0) {
+        Fe fin[NP];
+#pragma unroll
+        for (int t = 0; t < NP; t++) fin[t] = s_fin[t];
+        finalize_evals<F, NP, TOOM>(fin, ra);
+        if (ra.mbox.world > 1) {
+#pragma unroll
+            for (int t = 0; t < NP; t++) s_fin[t] = fin[t];
+        } else {
+            publish_raw<F, NP>(fin, ra);
+        }
+    }
+    if (ra.mbox.world > 1) {  // uniform over the block
+        __syncthreads();
+        const bool ok = mailbox_allreduce<F, NP>(s_fin, s_in, &s_ok, ra.mbox);
+        if (threadIdx.x == 0) {
+            Fe fin[NP];
+#pragma unroll
+            for (int t = 0; t < NP; t++) fin[t] = s_fin[t];
+            publish_raw<F, NP>(fin, ra, ok ? 0u : kMailboxTimeoutFlag);
+        }
+    }
 }
 
 template <class F, int NP, bool TOOM = false>
@@ -139,29 +261,7 @@ __device__ __forceinline__ void reduce_publish(Fe* acc, const ReduceArgs& ra) {
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        Fe fin[NP];
-#pragma unroll
-        for (int t = 0; t < NP; t++) fin[t] = s_fin[t];
-        if (ra.skip1 && NP > 1) fin[1] = fe_sub<F>(ra.claim, fin[0]);
-        if (TOOM) toom_to_evals<F>(fin);
-#pragma unroll
-        for (int t = 0; t < NP; t++) {
-            st_fe(ra.result_dev + ra.out_slot + t, fin[t]);
-            st_fe(ra.result_host + ra.out_slot + t, fin[t]);
-            if (ra.lanes) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) ra.lanes[(ra.out_slot + t) * 8 + i] = fin[t].v[i];
-            }
-        }
-        *ra.ticket = 0;  // ready for the next launch on this stream
-        ra.ticket[kWorkCounterOffset] = 0;
-        __threadfence_system();
-        if (ra.seq != 0) {
-            *(volatile unsigned*)ra.flag_host = ra.seq;
-            __threadfence_system();
-        }
-    }
+    finish_last_block<F, NP, TOOM>(s_fin, ra);
 }
 
 // ---- launch helpers ----------------------------------------------------------------------------
@@ -180,7 +280,7 @@ inline unsigned grid_for(uint64_t items, int threads, int num_sms, int bpsm) {
 }
 
 inline ReduceArgs make_ra(const ReduceScratch& s, int slot) {
-    return ReduceArgs{s.block_partials, s.ticket, s.result_dev, s.result_host_devptr, slot, s.flag_host_devptr, s.seq, s.lanes, 0, Fe{}};
+    return ReduceArgs{s.block_partials, s.ticket, s.result_dev, s.result_host_devptr, slot, s.flag_host_devptr, s.seq, s.lanes, 0, Fe{}, s.mbox};
 }
 
 // host: the multiples r * 2^(32 i + 64) mod p the kernels' fe_mul_fixed consumes (r in Montgomery form)
