@@ -575,7 +575,7 @@ def run_ours(args):
         "roofline": roofline, "cpu_baseline": cpu, "prove_ms": ms_per_step, "proof_keccak": proof_digest, "verified": verified,
         "proof_equals_cpu_oracle_golden": golden_parity, "golden_oracle": res["golden_oracle"],
         "round_kernel_ms": [round(x, 4) for x in main_round_ms], "step_ms": [round(x, 3) for x in step_ms], "microbench": mb,
-        "config4": config4, "ntt": ntt,
+        "config4": config4, "ntt": ntt, "uses_mailbox": (ctx.uses_mailbox() if world > 1 else None),
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

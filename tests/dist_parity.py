@@ -118,7 +118,7 @@ def main():
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(json.dumps({"dist_parity": bool(flag.item()), "world": world, "checks": checks}), flush=True)
+        print(json.dumps({"dist_parity": bool(flag.item()), "world": world, "checks": checks, "uses_mailbox": sctx.uses_mailbox()}), flush=True)
     dist.destroy_process_group()
     return 0 if flag.item() else 1
 
