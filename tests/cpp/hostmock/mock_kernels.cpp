@@ -28,7 +28,7 @@ namespace {
 thread_local const host::Field* g_field = nullptr;
 thread_local host::El g_challenge;
 thread_local std::vector<host::El> g_sums;
-alignas(32) thread_local uint4 sop_smem[2 * 2 * kMaxFactors * 128 + 5 * (4 * 128 + 128 / 4)];  // e/d arrays + wide accumulators (D <= 4)
+alignas(32) thread_local uint4 sop_smem[2 * 2 * (kMaxFactors + kMaxVirtual) * 128 + 5 * (4 * 128 + 128 / 4)];  // e/d arrays + wide accumulators (D <= 4)
 constexpr int kThreads = 128;
 
 inline host::El el(const Fe& a) { host::El e; std::memcpy(e.v, a.v, 32); return e; }
@@ -50,6 +50,9 @@ inline Fe ld_fe_stream(const Fe* p) { return *p; }
 inline void st_fe(Fe* p, const Fe& v) { *p = v; }
 #include "../host_accw.hpp"
 struct ReduceArgs { int skip1; };
+// hooks of sop_kernel.cuh's dynamic work distribution: never reached in the sequential replay (DYN = false)
+inline uint32_t sop_fetch_chunk(const ReduceArgs&) { std::abort(); }
+inline uint32_t sop_bcast_lane0(uint32_t v) { return v; }
 template <class F, int NP>
 void reduce_publish(const Fe* acc, const ReduceArgs&) {
     for (int t = 0; t < NP; t++) g_sums[(size_t)t] = g_field->add(g_sums[(size_t)t], el(acc[t]));
@@ -59,6 +62,7 @@ void reduce_publish(const Fe* acc, const ReduceArgs&) {
 
 #include "ntt_sharded_kernels.cuh"
 #include "sop_kernel.cuh"
+#include "sop_group.hpp"
 
 namespace zk {
 namespace {
@@ -165,7 +169,7 @@ cudaError_t launch_product_sum(int field, const TablePtrs& tabs, int m, uint64_t
 
 // ---- sum of products: the real kernel source, replayed
 template <class FT, int D>
-cudaError_t sop_replay(int field, const TablePtrs& tabs, const SopSpec& spec, uint64_t q, bool fold, const Fe& r,
+cudaError_t sop_replay(int field, const TablePtrs& tabs, const SopSpec& spec_in, uint64_t q, bool fold, const Fe& r,
                        const ReduceScratch& s, const Fe* claim) {
     const Field F(field);
     g_field = &F;
@@ -173,8 +177,10 @@ cudaError_t sop_replay(int field, const TablePtrs& tabs, const SopSpec& spec, ui
     g_sums.assign((size_t)D + 1, F.zero());
     const unsigned grid = 3;
     const int skip1 = (fold && claim) ? 1 : 0;
-    const char* wide_env = std::getenv("ZK_B200_SOP_WIDE");  // the same knob the product launcher reads
-    if (wide_env && wide_env[0] == '1') {
+    const char* wide_env = std::getenv("ZK_B200_SOP_WIDE");  // the same knobs the product launcher reads (kernels_sop.cu)
+    const char* group_env = std::getenv("ZK_B200_SOP_GROUP");
+    const SopSpec spec = (group_env && group_env[0] == '0') ? spec_in : sop_group(spec_in);  // common factors, like the launcher
+    if (!(wide_env && wide_env[0] == '0')) {
         // the deferred-reduction variant: block by block, shared memory cleared first (the kernel's accw_zero +
         // __syncthreads(), which a thread-by-thread replay cannot interleave)
         for (unsigned b = 0; b < grid; b++) {

@@ -33,7 +33,7 @@ host::El g_challenge;                       // the launch-wide fold multiplier (
 std::vector<host::El> g_sums;               // what reduce_publish would publish
 // shared memory of one block, sized by the harness exactly as the launcher does (kernels_sop.cu: sop_smem_total) and
 // followed by guard words: a carve-up that runs past the launch's allocation is caught
-constexpr size_t kSmemMaxUint4 = 2 * 2 * kMaxFactors * kThreads + 5 * (4 * kThreads + kThreads / 4) + 64;
+constexpr size_t kSmemMaxUint4 = 2 * 2 * (kMaxFactors + kMaxVirtual) * kThreads + 5 * (4 * kThreads + kThreads / 4) + 64;
 alignas(32) uint4 sop_smem[kSmemMaxUint4];
 
 inline host::El el(const Fe& a) { host::El e; std::memcpy(e.v, a.v, 32); return e; }
@@ -54,6 +54,9 @@ template <class F> void fe_fold_fixed_f64_x2(Fe& lo, Fe& hi, const Fe& x0, const
 }
 #include "host_accw.hpp"
 struct ReduceArgs { int skip1; };
+// hooks of the dynamic work distribution: never reached in the sequential replay (DYN = false)
+inline uint32_t sop_fetch_chunk(const ReduceArgs&) { std::abort(); }
+inline uint32_t sop_bcast_lane0(uint32_t v) { return v; }
 template <class F, int NP>
 void reduce_publish(const Fe* acc, const ReduceArgs&) {  // the harness applies S(1) = claim - S(0) after the last block
     for (int t = 0; t < NP; t++) g_sums[(size_t)t] = g_field->add(g_sums[(size_t)t], el(acc[t]));
@@ -63,6 +66,7 @@ void reduce_publish(const Fe* acc, const ReduceArgs&) {  // the harness applies 
 }  // namespace zk
 
 #include "sop_kernel.cuh"
+#include "sop_group.hpp"
 
 using zk::Fe;
 using zk::host::El;
@@ -86,7 +90,7 @@ static void replay(const zk::TablePtrs& tabs, const zk::SopSpec& spec, uint64_t 
     gridDim = dim3(grid, 1, 1);
     blockDim = dim3(zk::kThreads, 1, 1);
     // what the launcher allocates for this launch, in uint4 units
-    const size_t used = ((size_t)2 * spec.n_tables * zk::kThreads * sizeof(zk::Fe) + (WIDE ? zk::accw_bytes(D + 1) : 0)) / sizeof(uint4);
+    const size_t used = ((size_t)2 * (spec.n_tables + spec.n_virt) * zk::kThreads * sizeof(zk::Fe) + (WIDE ? zk::accw_bytes(D + 1) : 0)) / sizeof(uint4);
     for (unsigned b = 0; b < grid; b++) {
         // a block starts with whatever the previous one left behind, except that the kernel's own accw_zero +
         // __syncthreads() happen before any accumulation: in this sequential replay that is a clear before the block
@@ -149,13 +153,16 @@ static long run_case(int field, unsigned log_len, bool fold, const zk::SopSpec& 
         tabs.t[k] = dev[(size_t)k].data();
     }
     zk::g_sums.assign((size_t)D + 1, F.zero());
+    // the kernel runs the launcher's GROUPED spec (common factors through virtual tables, sop_group.hpp); the naive model
+    // above evaluated the original terms
+    const zk::SopSpec kspec = zk::sop_group(spec);
     // mode 0: every evaluation summed, integer folds; 1: S(1) derived from the claim; 2: S(1) derived, FP64 folds;
     // 3: deferred reduction (WIDE), every evaluation summed; 4: WIDE with S(1) derived
-    if (fold && mode == 2) replay<FT, D, true, true, false>(tabs, spec, len / 4, grid, 1);
-    else if (fold && mode >= 3) replay<FT, D, true, false, true>(tabs, spec, len / 4, grid, mode == 4);
-    else if (fold) replay<FT, D, true, false, false>(tabs, spec, len / 4, grid, mode == 1);
-    else if (mode >= 3) replay<FT, D, false, false, true>(tabs, spec, len / 2, grid, 1);
-    else replay<FT, D, false, false, false>(tabs, spec, len / 2, grid, 1 /* ignored without a fold */);
+    if (fold && mode == 2) replay<FT, D, true, true, false>(tabs, kspec, len / 4, grid, 1);
+    else if (fold && mode >= 3) replay<FT, D, true, false, true>(tabs, kspec, len / 4, grid, mode == 4);
+    else if (fold) replay<FT, D, true, false, false>(tabs, kspec, len / 4, grid, mode == 1);
+    else if (mode >= 3) replay<FT, D, false, false, true>(tabs, kspec, len / 2, grid, 1);
+    else replay<FT, D, false, false, false>(tabs, kspec, len / 2, grid, 1 /* ignored without a fold */);
     if (fold && (mode == 1 || mode == 2 || mode == 4)) {  // what the last block does with ra.claim = S(0) + S(1)
         long untouched = (zk::g_sums[1] != F.zero());
         zk::g_sums[1] = F.sub(F.add(want[0], want[1]), zk::g_sums[0]);
@@ -187,6 +194,16 @@ int main() {
     const zk::SopSpec sq = make_spec(2, {{0, 0}, {1}});
     const zk::SopSpec wide = make_spec(8, {{0, 1}, {2, 3}, {4, 5}, {6, 7}, {0, 7}, {1, 6}, {2, 5}, {3, 4}});
     const zk::SopSpec one = make_spec(3, {{0, 1, 2}});
+    // shapes the launcher factors: x.a + x.b -> x.(a + b)
+    const zk::SopSpec fan = make_spec(4, {{0, 1}, {0, 2}, {0, 3}});
+    const zk::SopSpec deep = make_spec(4, {{0, 1, 2}, {1, 0, 3}, {1, 2}, {3, 3}});
+    {
+        const zk::SopSpec g = zk::sop_group(gkr), f = zk::sop_group(fan), d = zk::sop_group(deep), w = zk::sop_group(wide);
+        if (g.n_terms != 2 || g.n_virt != 1 || f.n_terms != 2 || f.n_virt != 1 || d.n_terms != 3 || d.n_virt != 1 || w.n_virt != 4 || w.n_terms != 4) {
+            std::printf("sop_group: unexpected factoring (%d,%d) (%d,%d) (%d,%d) (%d,%d)\n", g.n_terms, g.n_virt, f.n_terms, f.n_virt, d.n_terms, d.n_virt, w.n_terms, w.n_virt);
+            return 1;
+        }
+    }
     for (int field = 0; field < 2; field++) {
         for (unsigned log_len = 1; log_len <= 11; log_len++) {
             for (int fold = 0; fold < 2; fold++) {
@@ -200,14 +217,18 @@ int main() {
                             bad += run_case<zk::Fr381, 2>(field, log_len, fold, wide, grid, mode);
                             bad += run_case<zk::Fr381, 4>(field, log_len, fold, one, grid, mode);
                             bad += run_case<zk::Fr381, 1>(field, log_len, fold, sq, grid, mode);
+                            bad += run_case<zk::Fr381, 2>(field, log_len, fold, fan, grid, mode);
+                            bad += run_case<zk::Fr381, 3>(field, log_len, fold, deep, grid, mode);
                         } else {
                             bad += run_case<zk::Fr377, 3>(field, log_len, fold, gkr, grid, mode);
                             bad += run_case<zk::Fr377, 2>(field, log_len, fold, sq, grid, mode);
                             bad += run_case<zk::Fr377, 2>(field, log_len, fold, wide, grid, mode);
                             bad += run_case<zk::Fr377, 4>(field, log_len, fold, one, grid, mode);
                             bad += run_case<zk::Fr377, 1>(field, log_len, fold, sq, grid, mode);
+                            bad += run_case<zk::Fr377, 2>(field, log_len, fold, fan, grid, mode);
+                            bad += run_case<zk::Fr377, 3>(field, log_len, fold, deep, grid, mode);
                         }
-                        cases += 5;
+                        cases += 7;
                     }
             }
         }

@@ -104,11 +104,16 @@ bool has_fused_path(int m, int degree);
 // reference's ProductPoly (polynomial/src/product_poly.rs:4-10, a pure product) cannot express.
 // A table may appear in several terms (and several times in one term); it is read — and folded — once per item.
 constexpr int kMaxTerms = 8;
+constexpr int kMaxVirtual = 4;
 struct SopSpec {
     int n_tables;                          // distinct tables, <= kMaxFactors
     int n_terms;                           // <= kMaxTerms
     uint8_t len[kMaxTerms];                // factors of term t, 1..kMaxFactors
-    uint8_t fac[kMaxTerms][kMaxFactors];   // table indices of term t
+    uint8_t fac[kMaxTerms][kMaxFactors];   // table indices of term t (>= n_tables: a virtual table)
+    // Launcher-made common factors (kernels_sop.cu: sop_group): virtual table n_tables + v = table virt_a[v] + table
+    // virt_b[v], so that x.a + x.b is evaluated as x.(a + b).  Never set by the C ABI's callers.
+    int n_virt;
+    uint8_t virt_a[kMaxVirtual], virt_b[kMaxVirtual];
 };
 bool sop_degree_supported(int degree);  // 1..4, like the fused product path
 // S(t) = sum_{j<half} sum_terms prod_k [A_k[j] + t (A_k[j+half] - A_k[j])], t = 0..degree  -> scratch.result_*

@@ -14,34 +14,71 @@
 // The per-item values e_k(t) = lo_k + t (hi_k - lo_k) of all tables live in shared memory (2 x n_tables elements per
 // thread) because the terms index them with run-time table numbers; the products run on the general fe_mul.
 // Rounds >= 1 derive S(1) from the previous round polynomial (one evaluation point less to multiply out) when
-// MAX_VAR_DEGREE covers the longest term; FP64 folds are wired behind ZK_B200_SOP_FOLD_PIPE.  No deferred
-// reduction or dynamic chunks yet (kernels_sumcheck.cu has those).
+// MAX_VAR_DEGREE covers the longest term.  Like the product kernels: the last product of every term goes unreduced
+// into wide per-thread accumulators (one Montgomery reduction per thread at the end), warps take their work from a global
+// chunk counter, and the running products of all D+1 evaluation points are multiplied side by side.  The launcher also
+// factors terms that differ in one table — add.Wb + add.Wc becomes add.(Wb + Wc) through a "virtual table" that the
+// kernel forms by one addition per item (sop_group below): the GKR layer costs 3 products per point instead of 4.
+// Knobs for A/B runs: ZK_B200_SOP_WIDE=0 (reduced products), ZK_B200_SOP_FOLD_PIPE=f64 (FP64 folds, with WIDE=0),
+// ZK_B200_SOP_GROUP=0 (no factoring), ZK_B200_SOP_SCHED=static.
 #include <atomic>
 #include <cstdlib>
 
 #include "kernels.h"
 #include "reduce.cuh"
 #include "accw.cuh"
+namespace zk {
+namespace {
+// hooks of sop_kernel.cuh's dynamic work distribution (the chunk counter sits next to the ticket, reduce.cuh)
+__device__ __forceinline__ uint32_t sop_fetch_chunk(const ReduceArgs& ra) { return atomicAdd(ra.ticket + kWorkCounterOffset, 1u); }
+__device__ __forceinline__ uint32_t sop_bcast_lane0(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+}  // namespace
+}  // namespace zk
 #include "sop_kernel.cuh"
+#include "sop_group.hpp"
 
 namespace zk {
 namespace {
 
-constexpr size_t sop_smem_bytes(int n_tables) { return (size_t)2 * n_tables * kThreads * sizeof(Fe); }
+constexpr size_t sop_smem_bytes(int n_slots) { return (size_t)2 * n_slots * kThreads * sizeof(Fe); }  // real + virtual tables
 
-constexpr size_t sop_smem_total(int n_tables, int np, bool wide) { return sop_smem_bytes(n_tables) + (wide ? accw_bytes(np) : 0); }
+constexpr size_t sop_smem_total(int n_slots, int np, bool wide) { return sop_smem_bytes(n_slots) + (wide ? accw_bytes(np) : 0); }
 
-template <class F, int D, bool FOLD, bool F64, bool WIDE>
+inline bool env_is(const char* name, char c) {
+    const char* e = std::getenv(name);
+    return e && e[0] == c;
+}
+// Which pipe folds: ZK_B200_SOP_FOLD_PIPE=int|f64 (default int: the FP64 variant measured 6 % slower on the GKR shape)
+inline bool sop_fold_on_f64() {
+    static const bool on = env_is("ZK_B200_SOP_FOLD_PIPE", 'f');
+    return on;
+}
+// Deferred reduction of every term's last product (default on; ZK_B200_SOP_WIDE=0 keeps the reduced products)
+inline bool sop_wide() {
+    static const bool on = !env_is("ZK_B200_SOP_WIDE", '0') && !sop_fold_on_f64();
+    return on;
+}
+inline bool sop_dynamic() {
+    static const bool on = !env_is("ZK_B200_SOP_SCHED", 's');
+    return on;
+}
+inline bool sop_grouping() {
+    static const bool on = !env_is("ZK_B200_SOP_GROUP", '0');
+    return on;
+}
+
+template <class F, int D, bool FOLD, bool F64, bool WIDE, bool DYN>
 cudaError_t do_sop_v(const TablePtrs& tabs, const SopSpec& spec, uint64_t q, const Fe& r, const ReduceScratch& s,
                      cudaStream_t st, const Fe* claim) {
-    const size_t smem = sop_smem_total(spec.n_tables, D + 1, WIDE);
-    static PerDeviceCache cache[kMaxFactors + 1];  // per device and table count (the shared-memory footprint depends on it)
-    const int bpsm = per_device(cache[spec.n_tables], [smem] {
-        cudaError_t e = cudaFuncSetAttribute(sop_round_kernel<F, D, FOLD, F64, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sop_smem_total(kMaxFactors, D + 1, WIDE));
+    const int slots = spec.n_tables + spec.n_virt;
+    const size_t smem = sop_smem_total(slots, D + 1, WIDE);
+    static PerDeviceCache cache[kMaxFactors + kMaxVirtual + 1];  // per device and slot count (the shared-memory footprint depends on it)
+    const int bpsm = per_device(cache[slots], [smem] {
+        cudaError_t e = cudaFuncSetAttribute(sop_round_kernel<F, D, FOLD, F64, WIDE, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sop_smem_total(kMaxFactors + kMaxVirtual, D + 1, WIDE));
         if (e != cudaSuccess) return -(int)e;
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sop_round_kernel<F, D, FOLD, F64, WIDE>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sop_round_kernel<F, D, FOLD, F64, WIDE, DYN>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
         return nb;
     });
     if (bpsm <= 0) return (cudaError_t)(-bpsm);
@@ -53,34 +90,20 @@ cudaError_t do_sop_v(const TablePtrs& tabs, const SopSpec& spec, uint64_t q, con
         ra.skip1 = 1;
         ra.claim = *claim;
     }
-    sop_round_kernel<F, D, FOLD, F64, WIDE><<<grid, kThreads, smem, st>>>(tabs, spec, q, tab, tab64, ra);
+    sop_round_kernel<F, D, FOLD, F64, WIDE, DYN><<<grid, kThreads, smem, st>>>(tabs, spec, q, tab, tab64, ra);
     return cudaGetLastError();
 }
 
-// Which pipe folds: ZK_B200_SOP_FOLD_PIPE=int|f64 (default int: the FP64 variant measured 6 % slower on the GKR shape)
-inline bool sop_fold_on_f64() {
-    static const bool on = [] {
-        const char* e = std::getenv("ZK_B200_SOP_FOLD_PIPE");
-        return e && e[0] == 'f';
-    }();
-    return on;
-}
-// ZK_B200_SOP_WIDE=1: deferred reduction of every term's last product (default off: written after the round's GPU
-// budget was spent — replayed on the host, not yet measured or run on hardware)
-inline bool sop_wide() {
-    static const bool on = [] {
-        const char* e = std::getenv("ZK_B200_SOP_WIDE");
-        return e && e[0] == '1';
-    }();
-    return on;
-}
-
 template <class F, int D, bool FOLD>
-cudaError_t do_sop(const TablePtrs& tabs, const SopSpec& spec, uint64_t q, const Fe& r, const ReduceScratch& s,
+cudaError_t do_sop(const TablePtrs& tabs, const SopSpec& spec_in, uint64_t q, const Fe& r, const ReduceScratch& s,
                    cudaStream_t st, const Fe* claim) {
-    if (sop_wide()) return do_sop_v<F, D, FOLD, false, true>(tabs, spec, q, r, s, st, claim);
-    if (FOLD && sop_fold_on_f64()) return do_sop_v<F, D, FOLD, FOLD, false>(tabs, spec, q, r, s, st, claim);
-    return do_sop_v<F, D, FOLD, false, false>(tabs, spec, q, r, s, st, claim);
+    const SopSpec spec = sop_grouping() ? sop_group(spec_in) : spec_in;
+    const bool dyn = sop_dynamic();
+    if (sop_wide())
+        return dyn ? do_sop_v<F, D, FOLD, false, true, true>(tabs, spec, q, r, s, st, claim) : do_sop_v<F, D, FOLD, false, true, false>(tabs, spec, q, r, s, st, claim);
+    if (FOLD && sop_fold_on_f64())
+        return dyn ? do_sop_v<F, D, FOLD, FOLD, false, true>(tabs, spec, q, r, s, st, claim) : do_sop_v<F, D, FOLD, FOLD, false, false>(tabs, spec, q, r, s, st, claim);
+    return dyn ? do_sop_v<F, D, FOLD, false, false, true>(tabs, spec, q, r, s, st, claim) : do_sop_v<F, D, FOLD, false, false, false>(tabs, spec, q, r, s, st, claim);
 }
 
 template <class F, bool FOLD>
