@@ -137,6 +137,25 @@ cudaError_t launch_round_poly(int field, const TablePtrs& tabs, int m, int degre
     publish(s, round_sums(F, tabs, m, degree, half));
     return cudaSuccess;
 }
+cudaError_t launch_round_poly_range(int field, const TablePtrs& tabs, int m, int degree, uint64_t count, uint64_t hoff,
+                                    const ReduceScratch& s, cudaStream_t, int* launches) {
+    const Field F(field);
+    ++*launches;
+    std::vector<El> S((size_t)degree + 1, F.zero());
+    for (int t = 0; t <= degree; t++) {
+        const El ft = F.from_u64((uint64_t)t);
+        for (uint64_t j = 0; j < count; j++) {
+            El pr = F.one();
+            for (int k = 0; k < m; k++) {
+                const El lo = el(tabs.t[k][j]), hi = el(tabs.t[k][j + hoff]);
+                pr = F.mul(pr, F.sub(lo, F.mul(ft, F.sub(lo, hi))));
+            }
+            S[(size_t)t] = F.add(S[(size_t)t], pr);
+        }
+    }
+    publish(s, S);
+    return cudaSuccess;
+}
 cudaError_t launch_fold(int field, const TablePtrs& tabs, int m, uint64_t half, const Fe& r, cudaStream_t, int* launches) {
     const Field F(field);
     ++*launches;
@@ -180,7 +199,7 @@ cudaError_t sop_replay(int field, const TablePtrs& tabs, const SopSpec& spec_in,
     const char* wide_env = std::getenv("ZK_B200_SOP_WIDE");  // the same knobs the product launcher reads (kernels_sop.cu)
     const char* group_env = std::getenv("ZK_B200_SOP_GROUP");
     const SopSpec spec = (group_env && group_env[0] == '0') ? spec_in : sop_group(spec_in);  // common factors, like the launcher
-    if (!(wide_env && wide_env[0] == '0')) {
+    if (wide_env && wide_env[0] == '1') {
         // the deferred-reduction variant: block by block, shared memory cleared first (the kernel's accw_zero +
         // __syncthreads(), which a thread-by-thread replay cannot interleave)
         for (unsigned b = 0; b < grid; b++) {

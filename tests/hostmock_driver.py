@@ -20,6 +20,8 @@ import ctypes as C
 
 import numpy as np
 
+os.environ.setdefault("ZK_B200_H2D_OVERLAP_MIN_LOG", "5")  # read once by the library: small tables take the sliced upload too
+
 import cref
 import zk_b200 as zk
 import zkoracle as O
@@ -103,6 +105,18 @@ def main():
     gsum = np.zeros(4, dtype=np.uint64)
     st = lib.zk_sumcheck_prove_host(ctx.h, 0, ptrs, m, n, d, None, 0, grp.ctypes.data, gch.ctypes.data, gfin.ctypes.data, gsum.ctypes.data)
     check(st == 0 and (grp == rp).all() and (gch == ch).all() and (gfin == fin).all() and (gsum == rsum).all(), "prove_host")
+    # the sliced upload with round 0 overlapped (ZK_B200_H2D_OVERLAP_MIN_LOG=5 below makes 2^6 .. 2^9 entries take it):
+    # a given claim, a wrong claim (it only enters the transcript), degree below / above the factor count, one table
+    for (n, m, d, wrong) in [(6, 3, 3, False), (9, 3, 3, True), (7, 2, 3, False), (8, 3, 2, False), (6, 1, 1, False), (5, 2, 2, False)]:
+        refs = [cref.gen_table(0, 11 + n, k, n) for k in range(m)]
+        rsum = cref.product_sum(0, refs, n)
+        if wrong:
+            rsum = cref.ints_to_mont(0, [cref.mont_to_ints(0, rsum.reshape(1, 4))[0] + 7])[0]
+        rp, ch, fin = cref.prove(0, refs, n, d, rsum, False)
+        ptrs = (C.c_void_p * m)(*[r.ctypes.data for r in refs])
+        grp = np.zeros((n, d + 1, 4), dtype=np.uint64); gch = np.zeros((n, 4), dtype=np.uint64); gfin = np.zeros((m, 4), dtype=np.uint64)
+        st = lib.zk_sumcheck_prove_host(ctx.h, 0, ptrs, m, n, d, rsum.ctypes.data, 0, grp.ctypes.data, gch.ctypes.data, gfin.ctypes.data, None)
+        check(st == 0 and (grp == rp).all() and (gch == ch).all() and (gfin == fin).all(), f"prove_host sliced n={n} m={m} d={d}")
 
     # ---- sum of products: api.cu + the real kernel source
     with open(os.path.join(ROOT, "tests", "golden", "sop_vectors.json")) as f:

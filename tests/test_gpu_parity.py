@@ -259,7 +259,8 @@ def test_prove_host_buffers_e2e(zk, ctx, cref):
 
     from zk_b200 import _ffi
 
-    for n, m, d in [(15, 3, 3), (17, 2, 2), (12, 3, 3), (17, 4, 4), (9, 1, 1), (15, 3, 3)]:
+    # 2^21 and 2^22 entries: the sliced upload with round 0 overlapped (api_sumcheck.cu); smaller: upload, then prove
+    for n, m, d in [(15, 3, 3), (17, 2, 2), (12, 3, 3), (17, 4, 4), (9, 1, 1), (15, 3, 3), (22, 3, 3), (21, 2, 2), (21, 1, 1), (21, 3, 2)]:
         refs = [cref.gen_table(0, 5 + n, k, n) for k in range(m)]
         claim = cref.product_sum(0, refs, n)
         rp, ch, fin = cref.prove(0, refs, n, d, claim, False, fast=True)
@@ -269,6 +270,12 @@ def test_prove_host_buffers_e2e(zk, ctx, cref):
                                                fin_g.ctypes.data, sum_g.ctypes.data)
         assert st == 0, (n, m, d)
         assert (sum_g == claim).all() and (rp_g == rp).all() and (ch_g == ch).all() and (fin_g == fin).all(), (n, m, d)
+        if n >= 21:  # a caller-supplied claim, wrong on purpose: it only enters the transcript (prover.rs:42)
+            bad = cref.ints_to_mont(0, [(cref.mont_to_ints(0, claim.reshape(1, 4))[0] + 5) % O.FIELDS[0].p])[0]
+            rp, ch, fin = cref.prove(0, refs, n, d, bad, False, fast=True)
+            st = _ffi.lib().zk_sumcheck_prove_host(ctx.h, 0, arr, m, n, d, bad.ctypes.data, 0, rp_g.ctypes.data, ch_g.ctypes.data,
+                                                   fin_g.ctypes.data, None)
+            assert st == 0 and (rp_g == rp).all() and (ch_g == ch).all() and (fin_g == fin).all(), (n, m, d, "wrong claim")
 
 
 # ---- properties at sizes the oracle does not reach ------------------------------------------------------------------

@@ -101,9 +101,9 @@ def test_gpu_suite_files_replayed_under_the_host_mock():
     assert r.returncode == 0 and " passed" in tail and "failed" not in tail, r.stdout[-3000:] + r.stderr[-2000:]
     assert int(tail.split(" passed")[0].split()[-1]) >= 80, tail
     assert "xpassed" not in tail and "xfailed" not in tail, tail
-    # the sum-of-products file once more with the plain reduced products (ZK_B200_SOP_WIDE=0; the deferred reduction is the default)
+    # the sum-of-products file once more with the deferred-reduction variant of the kernel source (ZK_B200_SOP_WIDE=1)
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", files[1]], capture_output=True, text=True,
-                       env=dict(env, ZK_B200_SOP_WIDE="0"), timeout=900, cwd=ROOT)
+                       env=dict(env, ZK_B200_SOP_WIDE="1"), timeout=900, cwd=ROOT)
     tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
     assert r.returncode == 0 and "14 passed" in tail, r.stdout[-3000:] + r.stderr[-2000:]
 

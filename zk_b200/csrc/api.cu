@@ -321,6 +321,7 @@ void zk_ctx_destroy(zk_ctx* c) {
     for (Fe* b : c->host_prove_buf) cudaFree(b);
     for (cudaStream_t s : c->copy_streams) cudaStreamDestroy(s);
     if (c->copy_done) cudaEventDestroy(c->copy_done);
+    for (cudaEvent_t ev : c->slice_events) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -74,6 +74,7 @@ struct zk_ctx {
     size_t eval_cap = 0;                  // elements
     std::vector<cudaStream_t> copy_streams;  // extra H2D streams of zk_sumcheck_prove_host (lazily created)
     cudaEvent_t copy_done = nullptr;
+    std::vector<cudaEvent_t> slice_events;   // zk_sumcheck_prove_host's overlapped round 0: copy-landed and kernel timing events per slice
     // device landing buffers of zk_sumcheck_prove_host, kept between calls (grow-only): a cudaMalloc + cudaFree of
     // gigabytes per proof is milliseconds of the host-buffer path and a device-wide synchronisation
     std::vector<Fe*> host_prove_buf;

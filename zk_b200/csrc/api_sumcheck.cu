@@ -115,9 +115,15 @@ struct ProveTimer {
 // The round loop of prover.rs:33-73.  `sop` == nullptr: the reference's ProductPoly (the m tables are the factors);
 // otherwise the polynomial is the sum of products `*sop` over the m tables — same transcript
 // protocol, same folds, only the round-sum kernels differ.
+// `round0` (optional, unsharded ProductPoly only): the sums of round 0, already computed by the caller while the tables
+// were still arriving (zk_sumcheck_prove_host) — the loop then starts at the first challenge.
+struct Round0 {
+    const uint64_t* sums;  // (degree + 1) elements
+    float kernel_ms;       // device time of the launches that produced them (reported as round 0's)
+};
 static int prove_core(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned degree, const uint64_t sum[4],
                       int absorb_initial_poly, uint64_t* round_polys_out, uint64_t* challenges_out,
-                      uint64_t* final_evals_out, const zk::SopSpec* sop) {
+                      uint64_t* final_evals_out, const zk::SopSpec* sop, const Round0* round0 = nullptr) {
     if (!ctx || !sum) return fail(ctx, ZK_ERR_INVALID_ARG);
     int st = product_check(ctx, tables, m, true);
     if (st == ZK_OK) st = distinct_check(ctx, tables, m);  // the prover consumes (folds in place) every listed table
@@ -197,7 +203,9 @@ static int prove_core(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
         return e;
     };
 
-    if (n > 0) {
+    if (n > 0 && round0 && !sharded && !sop) {
+        std::memcpy(S.data(), round0->sums, (size_t)np * 32);
+    } else if (n > 0) {
         if (sharded && (cur_len < 2 || cur_len <= ctx->gather_threshold)) {
             st = gather();
             if (st != ZK_OK) return st;
@@ -280,6 +288,10 @@ static int prove_core(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
             CU(ctx, cudaMemcpyAsync(final_evals_out + 4 * (size_t)k, cur.t[k], 32, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n > 0 && round0 && ctx->world == 1 && !sop) {
+        ctx->round_ms.push_back(round0->kernel_ms);
+        ctx->prove_ms[2] += round0->kernel_ms;
+    }
     for (size_t i = 0; i + 1 < ev; i += 2) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ctx->events[i], ctx->events[i + 1]) == cudaSuccess) {
@@ -341,6 +353,71 @@ int zk_sumcheck_prove_host(zk_ctx* ctx, int field, const uint64_t* const* host_t
         }
         tabs[k] = new (std::nothrow) zk_table{ctx, field, n_vars, local_len, ctx->host_prove_buf[k], ctx->host_prove_cap[k]};
         if (!tabs[k]) { st = fail(ctx, ZK_ERR_OOM); break; }
+    }
+    // Round 0 overlapped with the upload (one GPU, prove_partial, fused path): the round sums are additive over index
+    // ranges, so the tables travel in slices of pairs — the low entries of slice c of every table on one copy stream, the
+    // high entries (j + N/2) on the other — and the round-0 kernel runs on slice c as soon as both halves have landed,
+    // while slice c + 1 is on the wire.  Only the last slice's kernel is left after the last byte: the 3 ms of round 0
+    // disappear behind the 116 ms of PCIe.  The per-slice sums are added on the host (exact modular additions).
+    // ZK_B200_H2D_OVERLAP=0 keeps the plain upload-then-prove order.
+    static const bool overlap_enabled = [] {
+        const char* e = std::getenv("ZK_B200_H2D_OVERLAP");
+        return !(e && e[0] == '0');
+    }();
+    static const unsigned overlap_min_log = [] {  // smallest local table (log2 entries) that is sliced; tests lower it
+        const char* e = std::getenv("ZK_B200_H2D_OVERLAP_MIN_LOG");
+        const int v = e ? std::atoi(e) : 21;
+        return (unsigned)(v < 5 ? 5 : (v > 40 ? 40 : v));
+    }();
+    const unsigned np = degree + 1;
+    const bool overlap = st == ZK_OK && overlap_enabled && world == 1 && !absorb_initial_poly && n_copy >= 2 && n_vars >= 1 &&
+                         local_len >= ((uint64_t)1 << overlap_min_log) && degree <= ZK_MAX_DEGREE && zk::has_fused_path((int)m, (int)degree);
+    std::vector<uint64_t> S0((size_t)np * 4, 0);
+    float round0_ms = 0;
+    if (overlap) {
+        const Field F(field);
+        const uint64_t half = local_len / 2;
+        const unsigned n_slices = 16;
+        const uint64_t slice = half / n_slices;
+        while (ctx->slice_events.size() < 4 * (size_t)n_slices) {
+            cudaEvent_t ev = nullptr;
+            CU(ctx, cudaEventCreateWithFlags(&ev, ctx->slice_events.size() < 2 * (size_t)n_slices ? cudaEventDisableTiming : cudaEventDefault));
+            ctx->slice_events.push_back(ev);
+        }
+        cudaError_t e = cudaSuccess;
+        for (unsigned c = 0; c < n_slices && e == cudaSuccess; c++) {  // every copy is queued up front
+            const uint64_t lo = c * slice;
+            for (int h = 0; h < 2 && e == cudaSuccess; h++) {
+                cudaStream_t cs = ctx->copy_streams[(size_t)h];
+                for (unsigned k = 0; k < m && e == cudaSuccess; k++)
+                    e = cudaMemcpyAsync(tabs[k]->data + h * half + lo, host_tables[k] + (h * half + lo) * 4, (size_t)slice * 32, cudaMemcpyHostToDevice, cs);
+                if (e == cudaSuccess) e = cudaEventRecord(ctx->slice_events[2 * c + h], cs);
+            }
+        }
+        if (e != cudaSuccess) st = cuda_fail(ctx, e, "upload");
+        El acc[ZK_MAX_DEGREE + 1];
+        for (unsigned t = 0; t < np; t++) acc[t] = F.zero();
+        std::vector<uint64_t> part((size_t)np * 4);
+        for (unsigned c = 0; c < n_slices && st == ZK_OK; c++) {
+            zk::TablePtrs p{};
+            for (unsigned k = 0; k < m; k++) p.t[k] = tabs[k]->data + c * slice;
+            e = cudaStreamWaitEvent(ctx->stream, ctx->slice_events[2 * c], 0);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->slice_events[2 * c + 1], 0);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->slice_events[2 * n_slices + 2 * c], ctx->stream);
+            next_seq(ctx, false);
+            if (e == cudaSuccess) e = zk::launch_round_poly_range(field, p, (int)m, (int)degree, slice, half, ctx->scratch, ctx->stream, &ctx->launches);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->slice_events[2 * n_slices + 2 * c + 1], ctx->stream);
+            if (e != cudaSuccess) { st = cuda_fail(ctx, e, "round 0 slice"); break; }
+            st = finish_reduction(ctx, field, (int)np, part.data(), false);
+            for (unsigned t = 0; t < np && st == ZK_OK; t++) acc[t] = F.add(acc[t], el_from(part.data() + 4 * t));
+        }
+        for (unsigned t = 0; t < np; t++) std::memcpy(S0.data() + 4 * t, acc[t].v, 32);
+        for (unsigned c = 0; c < n_slices && st == ZK_OK; c++) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ctx->slice_events[2 * n_slices + 2 * c], ctx->slice_events[2 * n_slices + 2 * c + 1]) == cudaSuccess) round0_ms += ms;
+        }
+    }
+    for (unsigned k = 0; k < m && st == ZK_OK && !overlap; k++) {
         cudaError_t e = cudaSuccess;
         if (n_copy == 1 || local_len < (uint64_t)n_copy * 4096) {
             e = cudaMemcpyAsync(tabs[k]->data, host_tables[k], (size_t)local_len * 32, cudaMemcpyHostToDevice, ctx->stream);
@@ -353,12 +430,29 @@ int zk_sumcheck_prove_host(zk_ctx* ctx, int field, const uint64_t* const* host_t
         }
         if (e != cudaSuccess) st = cuda_fail(ctx, e, "upload");
     }
-    if (st == ZK_OK && n_copy > 1) {
+    if (st == ZK_OK && n_copy > 1 && !overlap) {
         for (cudaStream_t s : ctx->copy_streams) {
             cudaError_t e = cudaEventRecord(ctx->copy_done, s);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0);
             if (e != cudaSuccess) { st = cuda_fail(ctx, e, "upload join"); break; }
         }
+    }
+    if (overlap) {
+        // the claimed sum: the caller's, or the true sum S_0(0) + S_0(1)
+        uint64_t claim[4];
+        if (st == ZK_OK) {
+            if (sum) std::memcpy(claim, sum, 32);
+            else {
+                const Field F(field);
+                const El c = F.add(el_from(S0.data()), el_from(S0.data() + 4));
+                std::memcpy(claim, c.v, 32);
+            }
+            if (sum_out) std::memcpy(sum_out, claim, 32);
+            const Round0 r0{S0.data(), round0_ms};
+            st = prove_core(ctx, tabs.data(), m, degree, claim, 0, round_polys_out, challenges_out, final_evals_out, nullptr, &r0);
+        }
+        free_all();
+        return st;
     }
     uint64_t claim[4];
     if (st == ZK_OK) {

@@ -82,6 +82,12 @@ struct ReduceScratch {
 // scratch.result_dev and scratch.result_host.
 cudaError_t launch_round_poly(int field, const TablePtrs& tabs, int m, int degree, uint64_t half,
                               const ReduceScratch& scratch, cudaStream_t stream, int* launches);
+// The same sums over the sub-range of `count` pairs (tabs.t[k][j], tabs.t[k][j + hoff]), j < count — a slice of a round
+// (the pointers are pre-offset to its first pair; hoff = the distance between the two entries of a pair = half the table).
+// Round sums are additive over index ranges: zk_sumcheck_prove_host overlaps round 0 with the host-to-device copies this way.
+// Fused paths only (has_fused_path).
+cudaError_t launch_round_poly_range(int field, const TablePtrs& tabs, int m, int degree, uint64_t count, uint64_t hoff,
+                                    const ReduceScratch& scratch, cudaStream_t stream, int* launches);
 // In-place fold of every factor at r (prover.rs:64 -> evaluation_form.rs:40-80 with initial_var = 0):
 // T[j] = T[j] - r (T[j] - T[j+half]), j < half.
 cudaError_t launch_fold(int field, const TablePtrs& tabs, int m, uint64_t half, const Fe& r, cudaStream_t stream,
@@ -125,6 +131,12 @@ cudaError_t launch_sop_round_poly(int field, const TablePtrs& tabs, const SopSpe
 cudaError_t launch_sop_fold_round_poly(int field, const TablePtrs& tabs, const SopSpec& spec, int degree,
                                        uint64_t n_prev, const Fe& r, const ReduceScratch& scratch, cudaStream_t stream,
                                        int* launches, const Fe* claim = nullptr);
+
+// The latency kernel of the small rounds (kernels_sumcheck.cu: round_small_kernel): the fused fold + round sums of a sum of
+// products over at most 4 tables with 8 lanes per item; applies when the round has few items (q = n_prev / 4).
+bool small_round_applies(int n_tables, int degree, uint64_t q);
+cudaError_t launch_small_fold_round(int field, const TablePtrs& tabs, const SopSpec& spec, int degree, uint64_t q, const Fe& r,
+                                    const ReduceScratch& scratch, cudaStream_t stream, int* launches, const Fe* claim);
 
 // ---- MLE utilities (kernels_mle.cu) --------------------------------------------------------------
 // General partial_evaluate step for variable `initial_var` of an nv-variable table: out[k] = fold of the

@@ -14,12 +14,12 @@
 // The per-item values e_k(t) = lo_k + t (hi_k - lo_k) of all tables live in shared memory (2 x n_tables elements per
 // thread) because the terms index them with run-time table numbers; the products run on the general fe_mul.
 // Rounds >= 1 derive S(1) from the previous round polynomial (one evaluation point less to multiply out) when
-// MAX_VAR_DEGREE covers the longest term.  Like the product kernels: the last product of every term goes unreduced
-// into wide per-thread accumulators (one Montgomery reduction per thread at the end), warps take their work from a global
-// chunk counter, and the running products of all D+1 evaluation points are multiplied side by side.  The launcher also
+// MAX_VAR_DEGREE covers the longest term.  Like the product kernels: warps take their work from a global chunk counter and
+// the running products of all D+1 evaluation points are multiplied side by side (the deferred reduction of the last
+// products exists as a variant, off by default: it costs more in occupancy than it saves here).  The launcher also
 // factors terms that differ in one table — add.Wb + add.Wc becomes add.(Wb + Wc) through a "virtual table" that the
 // kernel forms by one addition per item (sop_group below): the GKR layer costs 3 products per point instead of 4.
-// Knobs for A/B runs: ZK_B200_SOP_WIDE=0 (reduced products), ZK_B200_SOP_FOLD_PIPE=f64 (FP64 folds, with WIDE=0),
+// Knobs for A/B runs: ZK_B200_SOP_WIDE=1 (deferred reduction), ZK_B200_SOP_FOLD_PIPE=f64 (FP64 folds),
 // ZK_B200_SOP_GROUP=0 (no factoring), ZK_B200_SOP_SCHED=static.
 #include <atomic>
 #include <cstdlib>
@@ -53,9 +53,11 @@ inline bool sop_fold_on_f64() {
     static const bool on = env_is("ZK_B200_SOP_FOLD_PIPE", 'f');
     return on;
 }
-// Deferred reduction of every term's last product (default on; ZK_B200_SOP_WIDE=0 keeps the reduced products)
+// Deferred reduction of every term's last product: ZK_B200_SOP_WIDE=1.  Default off — measured on the GKR shape (4 x 2^24,
+// profiles/r02_sop_variants.txt): its 34 KB of accumulators per block leave 3 resident blocks instead of 4 and the proof
+// takes 5.19 ms against 4.73 ms with reduced products (the product kernels, with fewer tables in shared memory, gain from it).
 inline bool sop_wide() {
-    static const bool on = !env_is("ZK_B200_SOP_WIDE", '0') && !sop_fold_on_f64();
+    static const bool on = env_is("ZK_B200_SOP_WIDE", '1') && !sop_fold_on_f64();
     return on;
 }
 inline bool sop_dynamic() {
@@ -144,6 +146,8 @@ cudaError_t launch_sop_fold_round_poly(int field, const TablePtrs& tabs, const S
                                        uint64_t n_prev, const Fe& r, const ReduceScratch& scratch, cudaStream_t stream,
                                        int* launches, const Fe* claim) {
     if (!spec_ok(spec) || n_prev < 4) return cudaErrorInvalidValue;
+    if (small_round_applies(spec.n_tables, degree, n_prev / 4))  // few items: the latency kernel (8 lanes per item)
+        return launch_small_fold_round(field, tabs, spec, degree, n_prev / 4, r, scratch, stream, launches, claim);
     ++*launches;
     return field == Fr381::ID ? do_sop_deg<Fr381, true>(tabs, spec, degree, n_prev / 4, r, scratch, stream, claim)
                               : do_sop_deg<Fr377, true>(tabs, spec, degree, n_prev / 4, r, scratch, stream, claim);

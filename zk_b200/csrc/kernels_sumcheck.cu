@@ -156,7 +156,7 @@ struct WarpChunks {  // 32-bit chunk ids: tables of up to 2^37 items
 // multiples of the challenge, one Montgomery row) instead of fe_mul_fixed's 76 wide multiplies.
 template <class F, int D, bool FOLD, bool TOOM = false, bool F64 = false, bool DYN = false>
 __global__ void __launch_bounds__(kThreads, (D <= 1) ? (FOLD ? ZK_RK_MINBLOCKS_D1 : ZK_RK_MINBLOCKS_D1 - 1) : (D == 2 ? ZK_RK_MINBLOCKS_D2 : ZK_RK_MINBLOCKS_D3))
-    round_kernel(TablePtrs tabs, int m, uint64_t q, const __grid_constant__ FixedMul rtab,
+    round_kernel(TablePtrs tabs, int m, uint64_t q, uint64_t hoff, const __grid_constant__ FixedMul rtab,
                  const __grid_constant__ FixedMulF64Sel rtab64, ReduceArgs ra) {
     static_assert(!TOOM || D == 3, "the Toom point set is wired for cubics");
     static_assert(!F64 || FOLD, "the FP64 variant only changes the folds");
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? (FOLD ? ZK_RK_MINBLOCKS_D
             }
         } else {
             n0 = ld_fe_stream(T + j0);
-            n1 = ld_fe_stream(T + j0 + q);
+            n1 = ld_fe_stream(T + j0 + hoff);
         }
     }
 #pragma unroll 1
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? (FOLD ? ZK_RK_MINBLOCKS_D
                     hi = n1;
                     if (nok) {
                         n0 = ld_fe_stream(NT + nj);
-                        n1 = ld_fe_stream(NT + nj + q);
+                        n1 = ld_fe_stream(NT + nj + hoff);
                     }
                 }
                 item_terms<F, D, TOOM>(k, k == m - 1, FOLD && ra.skip1 != 0, lo, hi, pr, accw);
@@ -310,7 +310,7 @@ inline bool fold_on_f64(int m) {
 }
 
 template <class F, int D, bool FOLD, bool TOOM, bool F64, bool DYN>
-cudaError_t do_round_v(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st, const Fe* claim) {
+cudaError_t do_round_v(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st, const Fe* claim, uint64_t hoff) {
     const FixedMul tab = (FOLD && !F64) ? make_fixed<F>(r) : FixedMul{};
     const FixedMulF64Sel tab64 = F64 ? make_fixed_f64<F>(r) : FixedMulF64Sel{};
     constexpr size_t smem = accw_bytes(D + 1);
@@ -329,24 +329,24 @@ cudaError_t do_round_v(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, co
         ra.skip1 = 1;
         ra.claim = *claim;
     }
-    round_kernel<F, D, FOLD, TOOM, F64, DYN><<<grid, kThreads, smem, st>>>(tabs, m, q, tab, tab64, ra);
+    round_kernel<F, D, FOLD, TOOM, F64, DYN><<<grid, kThreads, smem, st>>>(tabs, m, q, hoff ? hoff : q, tab, tab64, ra);
     return cudaGetLastError();
 }
 template <class F, int D, bool FOLD, bool TOOM = false>
-cudaError_t do_round(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st, const Fe* claim) {
+cudaError_t do_round(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st, const Fe* claim, uint64_t hoff) {
     const bool dyn = m >= 2 && dynamic_chunks();
     if (FOLD && fold_on_f64(m))
-        return dyn ? do_round_v<F, D, FOLD, TOOM, FOLD, true>(tabs, m, q, r, s, st, claim) : do_round_v<F, D, FOLD, TOOM, FOLD, false>(tabs, m, q, r, s, st, claim);
-    return dyn ? do_round_v<F, D, FOLD, TOOM, false, true>(tabs, m, q, r, s, st, claim) : do_round_v<F, D, FOLD, TOOM, false, false>(tabs, m, q, r, s, st, claim);
+        return dyn ? do_round_v<F, D, FOLD, TOOM, FOLD, true>(tabs, m, q, r, s, st, claim, hoff) : do_round_v<F, D, FOLD, TOOM, FOLD, false>(tabs, m, q, r, s, st, claim, hoff);
+    return dyn ? do_round_v<F, D, FOLD, TOOM, false, true>(tabs, m, q, r, s, st, claim, hoff) : do_round_v<F, D, FOLD, TOOM, false, false>(tabs, m, q, r, s, st, claim, hoff);
 }
 template <class F, bool FOLD>
 cudaError_t do_round_deg(const TablePtrs& tabs, int m, int degree, uint64_t q, const Fe& r, const ReduceScratch& s,
-                         cudaStream_t st, const Fe* claim = nullptr) {
+                         cudaStream_t st, const Fe* claim = nullptr, uint64_t hoff = 0) {
     switch (degree) {
-        case 1: return do_round<F, 1, FOLD>(tabs, m, q, r, s, st, claim);
-        case 2: return do_round<F, 2, FOLD>(tabs, m, q, r, s, st, claim);
-        case 3: return m == 3 ? do_round<F, 3, FOLD, true>(tabs, m, q, r, s, st, claim) : do_round<F, 3, FOLD>(tabs, m, q, r, s, st, claim);
-        case 4: return do_round<F, 4, FOLD>(tabs, m, q, r, s, st, claim);
+        case 1: return do_round<F, 1, FOLD>(tabs, m, q, r, s, st, claim, hoff);
+        case 2: return do_round<F, 2, FOLD>(tabs, m, q, r, s, st, claim, hoff);
+        case 3: return m == 3 ? do_round<F, 3, FOLD, true>(tabs, m, q, r, s, st, claim, hoff) : do_round<F, 3, FOLD>(tabs, m, q, r, s, st, claim, hoff);
+        case 4: return do_round<F, 4, FOLD>(tabs, m, q, r, s, st, claim, hoff);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -363,8 +363,13 @@ cudaError_t do_round_deg(const TablePtrs& tabs, int m, int degree, uint64_t q, c
 // (any exact evaluation of prover.rs:49-56 / :64 is), so which kernel a round takes is invisible in the proof.
 // m <= 4 (2m fold lanes) and D <= 4; other shapes stay on the streaming kernel.
 constexpr int kSmallGroup = 8;
+// The polynomial is given as a sum of products (SopSpec; a ProductPoly is the single term 0.1...m-1), so the same kernel
+// serves the small rounds of the sum-of-products prover (kernels_sop.cu): lane t walks the terms, fetching lo_f / hi_f of
+// each factor from the lanes that folded them.
 template <class F, int D>
-__global__ void __launch_bounds__(kThreads) round_small_kernel(TablePtrs tabs, int m, uint64_t q, Fe r_in, ReduceArgs ra) {
+__global__ void __launch_bounds__(kThreads)
+    round_small_kernel(TablePtrs tabs, const __grid_constant__ SopSpec spec, uint64_t q, Fe r_in, ReduceArgs ra) {
+    const int m = spec.n_tables;
     constexpr int NP = D + 1;
     __shared__ Fe sh[kWarps][kSmallGroup];
     __shared__ Fe sh_fin[kThreads / kSmallGroup][kSmallGroup];
@@ -389,28 +394,34 @@ __global__ void __launch_bounds__(kThreads) round_small_kernel(TablePtrs tabs, i
             v = fe_fold<F>(a, b, r);  // a - r (a - b): evaluation_form.rs:68
             st_fe(T, v);
         }
-        Fe pr = fe_zero<F>();
+        Fe tot = fe_zero<F>();
 #pragma unroll 1
-        for (int k = 0; k < m; k++) {
-            Fe lo, hi;
+        for (int term = 0; term < spec.n_terms; term++) {
+            Fe pr = fe_zero<F>();
+#pragma unroll 1
+            for (int fi = 0; fi < (int)spec.len[term]; fi++) {
+                const int k = spec.fac[term][fi];
+                Fe lo, hi;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                lo.v[i] = __shfl_sync(0xffffffffu, v.v[i], base + 2 * k);
-                hi.v[i] = __shfl_sync(0xffffffffu, v.v[i], base + 2 * k + 1);
-            }
-            // e = e_k(g): lo, hi, hi + d, hi + 2d, ...
-            Fe e = (g == 0) ? lo : hi;
-            if (D >= 2) {
-                const Fe d = fe_sub<F>(hi, lo);
-#pragma unroll
-                for (int t = 2; t <= D; t++) {
-                    const Fe e2 = fe_add<F>(e, d);
-                    if (g >= t) e = e2;
+                for (int i = 0; i < 8; i++) {
+                    lo.v[i] = __shfl_sync(0xffffffffu, v.v[i], base + 2 * k);
+                    hi.v[i] = __shfl_sync(0xffffffffu, v.v[i], base + 2 * k + 1);
                 }
+                // e = e_k(g): lo, hi, hi + d, hi + 2d, ...
+                Fe e = (g == 0) ? lo : hi;
+                if (D >= 2) {
+                    const Fe d = fe_sub<F>(hi, lo);
+#pragma unroll
+                    for (int t = 2; t <= D; t++) {
+                        const Fe e2 = fe_add<F>(e, d);
+                        if (g >= t) e = e2;
+                    }
+                }
+                pr = (fi == 0) ? e : fe_mul<F>(pr, e);
             }
-            pr = (k == 0) ? e : fe_mul<F>(pr, e);
+            tot = (term == 0) ? pr : fe_add<F>(tot, pr);
         }
-        if (live && g < NP && !(skip1 && g == 1)) acc = fe_add<F>(acc, pr);
+        if (live && g < NP && !(skip1 && g == 1)) acc = fe_add<F>(acc, tot);
     }
     // warp: the four groups' lanes of the same point
 #pragma unroll
@@ -476,7 +487,7 @@ inline uint64_t small_q_threshold() {
     return v;
 }
 template <class F, int D>
-cudaError_t do_round_small_d(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st, const Fe* claim) {
+cudaError_t do_round_small_d(const TablePtrs& tabs, const SopSpec& spec, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st, const Fe* claim) {
     const uint64_t per_block = kThreads / kSmallGroup;
     uint64_t need = (q + per_block - 1) / per_block;
     const uint64_t cap = (uint64_t)s.num_sms * 16 < (uint64_t)kMaxGridBlocks ? (uint64_t)s.num_sms * 16 : (uint64_t)kMaxGridBlocks;
@@ -486,19 +497,27 @@ cudaError_t do_round_small_d(const TablePtrs& tabs, int m, uint64_t q, const Fe&
         ra.skip1 = 1;
         ra.claim = *claim;
     }
-    round_small_kernel<F, D><<<(unsigned)(need < cap ? need : cap), kThreads, 0, st>>>(tabs, m, q, r, ra);
+    round_small_kernel<F, D><<<(unsigned)(need < cap ? need : cap), kThreads, 0, st>>>(tabs, spec, q, r, ra);
     return cudaGetLastError();
 }
 template <class F>
-cudaError_t do_round_small(const TablePtrs& tabs, int m, int degree, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st,
+cudaError_t do_round_small(const TablePtrs& tabs, const SopSpec& spec, int degree, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st,
                            const Fe* claim) {
     switch (degree) {
-        case 1: return do_round_small_d<F, 1>(tabs, m, q, r, s, st, claim);
-        case 2: return do_round_small_d<F, 2>(tabs, m, q, r, s, st, claim);
-        case 3: return do_round_small_d<F, 3>(tabs, m, q, r, s, st, claim);
-        case 4: return do_round_small_d<F, 4>(tabs, m, q, r, s, st, claim);
+        case 1: return do_round_small_d<F, 1>(tabs, spec, q, r, s, st, claim);
+        case 2: return do_round_small_d<F, 2>(tabs, spec, q, r, s, st, claim);
+        case 3: return do_round_small_d<F, 3>(tabs, spec, q, r, s, st, claim);
+        case 4: return do_round_small_d<F, 4>(tabs, spec, q, r, s, st, claim);
         default: return cudaErrorInvalidValue;
     }
+}
+inline SopSpec product_as_spec(int m) {  // ProductPoly = the single term 0.1...(m-1)
+    SopSpec sp{};
+    sp.n_tables = m;
+    sp.n_terms = 1;
+    sp.len[0] = (uint8_t)m;
+    for (int k = 0; k < m; k++) sp.fac[0][k] = (uint8_t)k;
+    return sp;
 }
 
 template <class F>
@@ -534,7 +553,7 @@ cudaError_t fold_round_poly_dispatch(const TablePtrs& tabs, int m, int degree, u
     const uint64_t q = n_prev / 4;
     if (has_fused_path(m, degree) && 2 * m <= kSmallGroup && q <= small_q_threshold()) {
         ++*launches;
-        return do_round_small<F>(tabs, m, degree, q, r, s, st, claim);
+        return do_round_small<F>(tabs, product_as_spec(m), degree, q, r, s, st, claim);
     }
     if (has_fused_path(m, degree)) { ++*launches; return do_round_deg<F, true>(tabs, m, degree, q, r, s, st, claim); }
     cudaError_t e = fold_dispatch<F>(tabs, m, n_prev / 2, r, &s, st, launches);
@@ -555,10 +574,27 @@ cudaError_t product_sum_dispatch(const TablePtrs& tabs, int m, uint64_t n, const
 
 bool has_fused_path(int m, int degree) { return m >= 1 && m <= kMaxFactors && degree >= 1 && degree <= 4; }
 
+bool small_round_applies(int n_tables, int degree, uint64_t q) {
+    return 2 * n_tables <= kSmallGroup && degree >= 1 && degree <= 4 && q <= small_q_threshold();
+}
+cudaError_t launch_small_fold_round(int field, const TablePtrs& tabs, const SopSpec& spec, int degree, uint64_t q, const Fe& r,
+                                    const ReduceScratch& scratch, cudaStream_t stream, int* launches, const Fe* claim) {
+    ++*launches;
+    return field == Fr381::ID ? do_round_small<Fr381>(tabs, spec, degree, q, r, scratch, stream, claim)
+                              : do_round_small<Fr377>(tabs, spec, degree, q, r, scratch, stream, claim);
+}
+
 cudaError_t launch_round_poly(int field, const TablePtrs& tabs, int m, int degree, uint64_t half,
                               const ReduceScratch& scratch, cudaStream_t stream, int* launches) {
     return field == Fr381::ID ? round_poly_dispatch<Fr381>(tabs, m, degree, half, scratch, stream, launches)
                               : round_poly_dispatch<Fr377>(tabs, m, degree, half, scratch, stream, launches);
+}
+cudaError_t launch_round_poly_range(int field, const TablePtrs& tabs, int m, int degree, uint64_t count, uint64_t hoff,
+                                    const ReduceScratch& scratch, cudaStream_t stream, int* launches) {
+    if (!has_fused_path(m, degree) || count < 1 || hoff < count) return cudaErrorInvalidValue;
+    ++*launches;
+    return field == Fr381::ID ? do_round_deg<Fr381, false>(tabs, m, degree, count, Fe{}, scratch, stream, nullptr, hoff)
+                              : do_round_deg<Fr377, false>(tabs, m, degree, count, Fe{}, scratch, stream, nullptr, hoff);
 }
 cudaError_t launch_fold(int field, const TablePtrs& tabs, int m, uint64_t half, const Fe& r, cudaStream_t stream,
                         int* launches) {
