@@ -58,13 +58,12 @@ inline double f64_fma(double a, double b, double c) { return __builtin_fma(a, b,
 }  // namespace detail
 
 // The two 16-bit halves of a limb as doubles.  Device: one I2F.F64.U16 each (conversion unit, the half is picked
-// by the instruction's .H0/.H1 selector) — or, with ZK_F64_MAGIC, the 2^52 + h bit pattern and one exact
-// subtraction on the FP64 pipe.  Host: plain conversions.  All exact.
+// by the instruction's .H0/.H1 selector).  Host: the 2^52 + h bit pattern and one exact subtraction.  All exact.
 #ifdef __CUDACC__
 __host__ __device__
 #endif
 inline void f64_halves(uint32_t x, double& lo, double& hi) {
-#if defined(__CUDA_ARCH__) && !defined(ZK_F64_MAGIC)
+#if defined(__CUDA_ARCH__)
     asm("{.reg .u16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.rn.f64.u16 %0, l;\n\tcvt.rn.f64.u16 %1, h;}" : "=d"(lo), "=d"(hi) : "r"(x));
 #else
     const double two52 = 4503599627370496.0;
