@@ -172,6 +172,7 @@ __device__ __forceinline__ void fe_fold_fixed_f64_x2(Fe& lo, Fe& hi, const Fe& x
     lo = f64_columns_reduce<F>(col[0], top0, true);
     hi = f64_columns_reduce<F>(col[1], top1, true);
 }
+
 template <class F>
 __device__ __forceinline__ Fe fe_fold_fixed_f64_add(const Fe& l, const Fe& h, const FixedMulF64& tab) {
     const Fe d = fe_sub<F>(h, l);
