@@ -87,16 +87,18 @@ class ClockSampler:
 
 
 def ncu_traffic(n, m, d, world):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch, from the committed `ncu --set full`
-    capture of this exact workload (profiles/); None for any other configuration."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (the first fused step), from the committed
+    `ncu --set full` capture of this exact workload (profiles/); None for any other configuration."""
     if not (n - (world.bit_length() - 1) == 26 and m == 3 and d == 3):
         return None, None
-    path = os.path.join(ROOT, "profiles", "r01_round_kernel_fold_D3_m3_n26_ncu_full.txt")
+    path = os.path.join(ROOT, "profiles", "r02_round_kernels_ncu_full.txt")
     try:
-        vals = {}
+        vals, fused = {}, False
         for line in open(path):
+            if line.startswith("Kernel Name"):
+                fused = "round_kernel<Fr381, 3, 1," in line  # FOLD = true: the fused fold + round-sum kernel
             for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                if line.startswith(key + " ["):
+                if fused and line.startswith(key + " ["):
                     unit = line.split("[")[1].split("]")[0]
                     v = float(line.split("=")[1].strip().replace(",", ""))
                     vals[key] = v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
@@ -363,7 +365,7 @@ def run_ours(args):
         """the CPU oracle's digest of the same full-size proof, committed offline (tests/golden/make_fullsize_digests.py)"""
         try:
             for c in json.load(open(os.path.join(ROOT, "tests", "golden", "fullsize_digests.json")))["cases"]:
-                if (c["log_n"], c["m"], c["degree"]) == (nn, m, d) and int(c["seed"], 16) == SEED:
+                if (c["log_n"], c["m"], c["degree"]) == (nn, m, d) and int(c["seed"], 16) == SEED and not c.get("absorb"):
                     return c
         except Exception:
             pass

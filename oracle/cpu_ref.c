@@ -341,12 +341,17 @@ EXPORT int zko_prove(int field, const uint64_t *const *tables, unsigned m, unsig
 /* Streamlined variant (same results, fused single pass per round, in place) for cross-checks at
  * sizes where the reference-shaped prover is too slow.  NOT the reported baseline. */
 EXPORT int zko_prove_fast(int field, uint64_t *const *tables, unsigned m, unsigned n_vars, unsigned degree,
-                          const uint64_t sum[4], uint64_t *round_polys_out, uint64_t *challenges_out,
+                          const uint64_t sum[4], int absorb, uint64_t *round_polys_out, uint64_t *challenges_out,
                           uint64_t *finals_out) {
     const field_t *F = &FIELDS[field];
     if (m > 8 || degree > 15) return -1;
     keccak_t tr; k_init(&tr);
-    uint8_t be[32]; fe s; memcpy(s.v, sum, 32); f_to_be32(&s, be, F); k_update(&tr, be, 32);
+    uint8_t be[32];
+    if (absorb) {                                                       /* `prove`: poly.to_bytes() first (prover.rs:16-17) */
+        const size_t n = (size_t)1 << n_vars;
+        for (unsigned k = 0; k < m; k++) for (size_t j = 0; j < n; j++) { f_to_be32(&((const fe *)tables[k])[j], be, F); k_update(&tr, be, 32); }
+    }
+    fe s; memcpy(s.v, sum, 32); f_to_be32(&s, be, F); k_update(&tr, be, 32);
     unsigned nv = n_vars;
     for (unsigned round = 0; round < n_vars; round++) {
         size_t half = (size_t)1 << (nv - 1);

@@ -124,12 +124,12 @@ def prove(field: int, tables, n_vars: int, degree: int, sum_mont: np.ndarray, ab
     fin = np.zeros((m, 4), dtype=np.uint64)
     sum_mont = np.ascontiguousarray(sum_mont, dtype=np.uint64)
     if fast:
-        assert not absorb
         work = [t.copy() for t in tables]
         if threads > 0:  # the streamlined prover on `threads` cores (pthreads), bit-identical
+            assert not absorb
             rc = lib().zko_prove_fast_mt(field, _ptr_array(work), m, n_vars, degree, _p(sum_mont), _p(rp), _p(ch), _p(fin), int(threads))
         else:
-            rc = lib().zko_prove_fast(field, _ptr_array(work), m, n_vars, degree, _p(sum_mont), _p(rp), _p(ch), _p(fin))
+            rc = lib().zko_prove_fast(field, _ptr_array(work), m, n_vars, degree, _p(sum_mont), int(bool(absorb)), _p(rp), _p(ch), _p(fin))
     else:
         rc = lib().zko_prove(field, _ptr_array(tables), m, n_vars, degree, _p(sum_mont), int(bool(absorb)), _p(rp), _p(ch),
                              _p(fin))

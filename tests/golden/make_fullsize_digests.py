@@ -56,8 +56,28 @@ def big(out_path, sizes):
         json.dump(doc, open(out_path, "w"), indent=1)
 
 
+def absorb_cases(out_path):
+    """BASELINE config 2 exactly: `prove` (the tables' to_bytes() absorbed first, prover.rs:16-17) of 2 tables x 2^24."""
+    doc = json.load(open(out_path))
+    for name, n, m, d in [("C2: prove WITH the initial-poly absorb, 2 tables 2^24, degree 2", 24, 2, 2), ("C1: prove WITH the absorb, single table 2^20", 20, 1, 1)]:
+        if any(c.get("absorb") and (c["log_n"], c["m"], c["degree"]) == (n, m, d) for c in doc["cases"]):
+            continue
+        t0 = time.time()
+        tabs = [cref.gen_table(FIELD, SEED, k, n) for k in range(m)]
+        claim = cref.product_sum(FIELD, tabs, n)
+        rp, ch, fin = cref.prove(FIELD, tabs, n, d, claim, True, fast=True)
+        doc["cases"].append({"name": name, "field": "bls12_381_fr", "seed": hex(SEED), "log_n": n, "m": m, "degree": d, "absorb": True,
+                             "claim_mont_limbs": [hex(int(x)) for x in claim], "proof_keccak": cref.keccak256(rp.tobytes() + ch.tobytes()).hex(),
+                             "finals_keccak": cref.keccak256(fin.tobytes()).hex(), "oracle": "zko_prove_fast (absorb)",
+                             "oracle_seconds": round(time.time() - t0, 1)})
+        print(doc["cases"][-1], flush=True)
+        json.dump(doc, open(out_path, "w"), indent=1)
+
+
 def main():
     out_path = sys.argv[1] if len(sys.argv) > 1 and sys.argv[1].endswith(".json") else os.path.join(ROOT, "tests", "golden", "fullsize_digests.json")
+    if "--absorb" in sys.argv:
+        return absorb_cases(out_path)
     if "--big" in sys.argv:
         return big(out_path, [int(x) for x in sys.argv[sys.argv.index("--big") + 1:]])
     res = []

@@ -39,9 +39,14 @@ def test_fullsize_proof_digest(zk, ctx, case):
     rp = np.zeros((n, d + 1, 4), dtype=np.uint64)
     ch = np.zeros((n, 4), dtype=np.uint64)
     fin = np.zeros((m, 4), dtype=np.uint64)
-    ctx.check(lib.zk_sumcheck_prove(ctx.h, pp._arr(), m, d, claim.ctypes.data, 0, rp.ctypes.data, ch.ctypes.data, fin.ctypes.data))
+    absorb = 1 if case.get("absorb") else 0  # `prove`: the tables' to_bytes() go through the host transcript first (prover.rs:16-17)
+    ctx.check(lib.zk_sumcheck_prove(ctx.h, pp._arr(), m, d, claim.ctypes.data, absorb, rp.ctypes.data, ch.ctypes.data, fin.ctypes.data))
     assert zk.keccak256(rp.tobytes() + ch.tobytes()).hex() == case["proof_keccak"]
     assert zk.keccak256(fin.tobytes()).hex() == case["finals_keccak"]
+    if absorb:  # verify (absorbs the polynomial again, verifier.rs:21-22) accepts it against fresh copies of the tables
+        fresh = zk.ProductPoly.new([zk.MultiLinearPolynomial.generate(n, k, seed=seed) for k in range(m)])
+        assert lib.zk_sumcheck_verify(ctx.h, fresh._arr(), m, claim.ctypes.data, rp.ctypes.data, n, d) == 0
+        return
     # and the proof is one the verifier accepts
     sub = np.zeros(4, dtype=np.uint64)
     vch = np.zeros((n, 4), dtype=np.uint64)
