@@ -53,7 +53,7 @@ struct ReduceArgs { int skip1; };
 // hooks of sop_kernel.cuh's dynamic work distribution: never reached in the sequential replay (DYN = false)
 inline uint32_t sop_fetch_chunk(const ReduceArgs&) { std::abort(); }
 inline uint32_t sop_bcast_lane0(uint32_t v) { return v; }
-template <class F, int NP>
+template <class F, int NP, bool TOOM = false>  // the mock replays the plain point set (TOOM = false)
 void reduce_publish(const Fe* acc, const ReduceArgs&) {
     for (int t = 0; t < NP; t++) g_sums[(size_t)t] = g_field->add(g_sums[(size_t)t], el(acc[t]));
 }

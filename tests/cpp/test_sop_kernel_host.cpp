@@ -57,8 +57,8 @@ struct ReduceArgs { int skip1; };
 // hooks of the dynamic work distribution: never reached in the sequential replay (DYN = false)
 inline uint32_t sop_fetch_chunk(const ReduceArgs&) { std::abort(); }
 inline uint32_t sop_bcast_lane0(uint32_t v) { return v; }
-template <class F, int NP>
-void reduce_publish(const Fe* acc, const ReduceArgs&) {  // the harness applies S(1) = claim - S(0) after the last block
+template <class F, int NP, bool TOOM = false>
+void reduce_publish(const Fe* acc, const ReduceArgs&) {  // the harness applies S(1) = claim - S(0) (and the Toom map) after the last block
     for (int t = 0; t < NP; t++) g_sums[(size_t)t] = g_field->add(g_sums[(size_t)t], el(acc[t]));
 }
 
@@ -85,7 +85,7 @@ static El rnd_el(const Field& F) {  // a product of two random words times a thi
 }
 
 static long g_guard_hits = 0;
-template <class FT, int D, bool FOLD, bool F64, bool WIDE>
+template <class FT, int D, bool FOLD, bool F64, bool WIDE, bool TOOM = false>
 static void replay(const zk::TablePtrs& tabs, const zk::SopSpec& spec, uint64_t q, unsigned grid, int skip1) {
     gridDim = dim3(grid, 1, 1);
     blockDim = dim3(zk::kThreads, 1, 1);
@@ -98,7 +98,7 @@ static void replay(const zk::TablePtrs& tabs, const zk::SopSpec& spec, uint64_t 
         for (unsigned t = 0; t < (unsigned)zk::kThreads; t++) {
             blockIdx = uint3{b, 0, 0};
             threadIdx = uint3{t, 0, 0};
-            zk::sop_round_kernel<FT, D, FOLD, F64, WIDE>(tabs, spec, q, zk::FixedMul{}, zk::FixedMulF64Sel{}, zk::ReduceArgs{skip1});
+            zk::sop_round_kernel<FT, D, FOLD, F64, WIDE, false, TOOM>(tabs, spec, q, zk::FixedMul{}, zk::FixedMulF64Sel{}, zk::ReduceArgs{skip1});
         }
         for (size_t i = used; i < zk::kSmemMaxUint4; i++) g_guard_hits += (zk::sop_smem[i].x != 0xDEADBEEFu || zk::sop_smem[i].w != 0xDEADBEEFu);
     }
@@ -157,18 +157,35 @@ static long run_case(int field, unsigned log_len, bool fold, const zk::SopSpec& 
     // above evaluated the original terms
     const zk::SopSpec kspec = zk::sop_group(spec);
     // mode 0: every evaluation summed, integer folds; 1: S(1) derived from the claim; 2: S(1) derived, FP64 folds;
-    // 3: deferred reduction (WIDE), every evaluation summed; 4: WIDE with S(1) derived
+    // 3: deferred reduction (WIDE), every evaluation summed; 4: WIDE with S(1) derived;
+    // 5 / 6 (D == 3, no term longer than 3): the Toom point set (0, 1, -1, infinity), all summed / S(1) derived
+    bool cubic_at_most = (D == 3);
+    for (int t = 0; t < spec.n_terms; t++) cubic_at_most = cubic_at_most && spec.len[t] <= 3;
+    const bool toom = mode >= 5;
+    if (toom && !cubic_at_most) return 0;
+    if (toom) {
+        constexpr bool T = (D == 3);
+        if (fold) replay<FT, D, true, false, false, T>(tabs, kspec, len / 4, grid, mode == 6);
+        else replay<FT, D, false, false, false, T>(tabs, kspec, len / 2, grid, 0);
+    } else
     if (fold && mode == 2) replay<FT, D, true, true, false>(tabs, kspec, len / 4, grid, 1);
     else if (fold && mode >= 3) replay<FT, D, true, false, true>(tabs, kspec, len / 4, grid, mode == 4);
     else if (fold) replay<FT, D, true, false, false>(tabs, kspec, len / 4, grid, mode == 1);
     else if (mode >= 3) replay<FT, D, false, false, true>(tabs, kspec, len / 2, grid, 1);
     else replay<FT, D, false, false, false>(tabs, kspec, len / 2, grid, 1 /* ignored without a fold */);
-    if (fold && (mode == 1 || mode == 2 || mode == 4)) {  // what the last block does with ra.claim = S(0) + S(1)
+    if (fold && (mode == 1 || mode == 2 || mode == 4 || mode == 6)) {  // what the last block does with ra.claim = S(0) + S(1)
         long untouched = (zk::g_sums[1] != F.zero());
         zk::g_sums[1] = F.sub(F.add(want[0], want[1]), zk::g_sums[0]);
         if (untouched) return 1000000;  // the t = 1 products were not skipped
     }
 
+    if (toom) {  // reduce.cuh: toom_to_evals — {S(0), S(1), S(-1), c3} -> S(0..3)
+        const El half = F.inverse(F.from_u64(2));
+        const El s0 = zk::g_sums[0], s1 = zk::g_sums[1], sm = zk::g_sums[2], c3 = zk::g_sums[3];
+        const El c2 = F.sub(F.mul(F.add(s1, sm), half), s0), c1 = F.sub(F.mul(F.sub(s1, sm), half), c3);
+        zk::g_sums[2] = F.add(F.add(s0, F.mul(F.from_u64(2), c1)), F.add(F.mul(F.from_u64(4), c2), F.mul(F.from_u64(8), c3)));
+        zk::g_sums[3] = F.add(F.add(s0, F.mul(F.from_u64(3), c1)), F.add(F.mul(F.from_u64(9), c2), F.mul(F.from_u64(27), c3)));
+    }
     long bad = 0;
     for (int t = 0; t <= D; t++) bad += (zk::g_sums[(size_t)t] != want[(size_t)t]);
     if (fold)  // the folded tables are the first half of the buffers, in place
@@ -209,8 +226,8 @@ int main() {
             for (int fold = 0; fold < 2; fold++) {
                 if (fold && log_len < 2) continue;  // the fused launch needs 4 entries
                 for (unsigned grid : {1u, 3u})
-                    for (int mode = 0; mode < 5; mode++) {
-                        if (!fold && mode != 0 && mode != 3) continue;
+                    for (int mode = 0; mode < 7; mode++) {
+                        if (!fold && mode != 0 && mode != 3 && mode != 5) continue;
                         if (field == 0) {
                             bad += run_case<zk::Fr381, 3>(field, log_len, fold, gkr, grid, mode);
                             bad += run_case<zk::Fr381, 2>(field, log_len, fold, sq, grid, mode);

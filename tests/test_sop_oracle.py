@@ -213,4 +213,4 @@ def test_sop_kernel_source_replayed_on_the_host(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300).stdout
-    assert "2016 cases, 0 mismatches, 0 guard hits" in out, out
+    assert "2884 cases, 0 mismatches, 0 guard hits" in out, out

@@ -64,23 +64,28 @@ inline bool sop_dynamic() {
     static const bool on = !env_is("ZK_B200_SOP_SCHED", 's');
     return on;
 }
+// Toom point set (0, 1, -1, infinity) for MAX_VAR_DEGREE 3 when no term has more than three factors (ZK_B200_SOP_TOOM=0: plain 0..3)
+inline bool sop_toom() {
+    static const bool on = !env_is("ZK_B200_SOP_TOOM", '0');
+    return on;
+}
 inline bool sop_grouping() {
     static const bool on = !env_is("ZK_B200_SOP_GROUP", '0');
     return on;
 }
 
-template <class F, int D, bool FOLD, bool F64, bool WIDE, bool DYN>
+template <class F, int D, bool FOLD, bool F64, bool WIDE, bool DYN, bool TOOM = false>
 cudaError_t do_sop_v(const TablePtrs& tabs, const SopSpec& spec, uint64_t q, const Fe& r, const ReduceScratch& s,
                      cudaStream_t st, const Fe* claim) {
     const int slots = spec.n_tables + spec.n_virt;
     const size_t smem = sop_smem_total(slots, D + 1, WIDE);
     static PerDeviceCache cache[kMaxFactors + kMaxVirtual + 1];  // per device and slot count (the shared-memory footprint depends on it)
     const int bpsm = per_device(cache[slots], [smem] {
-        cudaError_t e = cudaFuncSetAttribute(sop_round_kernel<F, D, FOLD, F64, WIDE, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(sop_round_kernel<F, D, FOLD, F64, WIDE, DYN, TOOM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sop_smem_total(kMaxFactors + kMaxVirtual, D + 1, WIDE));
         if (e != cudaSuccess) return -(int)e;
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sop_round_kernel<F, D, FOLD, F64, WIDE, DYN>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sop_round_kernel<F, D, FOLD, F64, WIDE, DYN, TOOM>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
         return nb;
     });
     if (bpsm <= 0) return (cudaError_t)(-bpsm);
@@ -92,7 +97,7 @@ cudaError_t do_sop_v(const TablePtrs& tabs, const SopSpec& spec, uint64_t q, con
         ra.skip1 = 1;
         ra.claim = *claim;
     }
-    sop_round_kernel<F, D, FOLD, F64, WIDE, DYN><<<grid, kThreads, smem, st>>>(tabs, spec, q, tab, tab64, ra);
+    sop_round_kernel<F, D, FOLD, F64, WIDE, DYN, TOOM><<<grid, kThreads, smem, st>>>(tabs, spec, q, tab, tab64, ra);
     return cudaGetLastError();
 }
 
@@ -101,6 +106,11 @@ cudaError_t do_sop(const TablePtrs& tabs, const SopSpec& spec_in, uint64_t q, co
                    cudaStream_t st, const Fe* claim) {
     const SopSpec spec = sop_grouping() ? sop_group(spec_in) : spec_in;
     const bool dyn = sop_dynamic();
+    if (D == 3 && sop_toom() && !sop_wide() && !(FOLD && sop_fold_on_f64()) && dyn) {  // the default configuration only
+        bool cubic_at_most = true;
+        for (int t = 0; t < spec.n_terms; t++) cubic_at_most &= spec.len[t] <= 3;
+        if (cubic_at_most) return do_sop_v<F, D, FOLD, false, false, true, D == 3>(tabs, spec, q, r, s, st, claim);
+    }
     if (sop_wide())
         return dyn ? do_sop_v<F, D, FOLD, false, true, true>(tabs, spec, q, r, s, st, claim) : do_sop_v<F, D, FOLD, false, true, false>(tabs, spec, q, r, s, st, claim);
     if (FOLD && sop_fold_on_f64())

@@ -27,11 +27,17 @@ namespace {
 // add.Wb + add.Wc = add.(Wb + Wc): one product less per evaluation point, the same field element by distributivity.
 // A term walks its factors once with the running products of ALL D+1 evaluation points in registers
 // (e_k(t+1) = e_k(t) + d_k between points): D+1 independent multiplications in flight per factor.
-template <class F, int D, bool FOLD, bool F64 = false, bool WIDE = false, bool DYN = false>
+// TOOM (D == 3, every term of at most 3 factors; the launcher checks): the four points are 0, 1, -1 and "infinity" (the
+// coefficient of t^3) instead of 0, 1, 2, 3 — e_k(-1) = lo_k - d_k, e_k(inf) = d_k — and a term of fewer than three factors
+// has no t^3 coefficient, so it is not multiplied out at infinity at all: the GKR layer add.(Wb + Wc) + mul.Wb.Wc costs 8
+// products per item instead of 9 (11 instead of 12 in round 0).  The last block maps the four sums back to S(0..3) with
+// exact field arithmetic (reduce.cuh: toom_to_evals, the product kernels' own), so the published values are the same.
+template <class F, int D, bool FOLD, bool F64 = false, bool WIDE = false, bool DYN = false, bool TOOM = false>
 __global__ void __launch_bounds__(kThreads)
     sop_round_kernel(TablePtrs tabs, const __grid_constant__ SopSpec spec, uint64_t q,
                      const __grid_constant__ FixedMul rtab, const __grid_constant__ FixedMulF64Sel rtab64, ReduceArgs ra) {
     static_assert(!F64 || FOLD, "the FP64 variant only changes the folds");
+    static_assert(!TOOM || D == 3, "the Toom point set is wired for cubics");
     const bool skip1 = FOLD && ra.skip1 != 0;
     extern __shared__ __align__(32) uint4 sop_smem[];  // Fe [2 * (n_tables + n_virt)][kThreads]: e_k then d_k; WIDE: + accumulators
     Fe* const ev = reinterpret_cast<Fe*>(sop_smem) + threadIdx.x;
@@ -90,35 +96,45 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll 1
             for (int term = 0; term < spec.n_terms; term++) {
                 const int len = (int)spec.len[term];
+                // Toom: point index 2 is t = -1, index 3 is "infinity", where only a term of exactly D factors has a value
+                const bool inf = !TOOM || len == D;
                 Fe p[D + 1];
                 {
                     const int f0 = spec.fac[term][0];
                     const Fe d = dv[(size_t)f0 * kThreads];
                     p[0] = ev[(size_t)f0 * kThreads];
+                    if (TOOM) {
+                        p[1] = fe_add<F>(p[0], d);
+                        p[2] = fe_sub<F>(p[0], d);
+                        p[3] = d;
+                    } else {
 #pragma unroll
-                    for (int t = 1; t <= D; t++) p[t] = fe_add<F>(p[t - 1], d);
+                        for (int t = 1; t <= D; t++) p[t] = fe_add<F>(p[t - 1], d);
+                    }
                 }
 #pragma unroll 1
                 for (int i = 1; i < len; i++) {
                     const int fi = spec.fac[term][i];
-                    Fe e = ev[(size_t)fi * kThreads];
+                    const Fe e0 = ev[(size_t)fi * kThreads];
                     const Fe d = dv[(size_t)fi * kThreads];
                     const bool last = (i == len - 1);
-                    if (WIDE && last) {
+                    Fe e = e0;
 #pragma unroll
-                        for (int t = 0; t <= D; t++) {
-                            if (t > 0) e = fe_add<F>(e, d);
-                            if (!(t == 1 && skip1)) {
-                                uint32_t w[16];
-                                fe_mul_wide(w, p[t], e);
-                                accw_add16(accw_at(accw, t), w);
-                            }
+                    for (int t = 0; t <= D; t++) {
+                        if (TOOM) {
+                            if (t == 1) e = fe_add<F>(e0, d);
+                            if (t == 2) e = fe_sub<F>(e0, d);
+                            if (t == 3) e = d;
+                        } else if (t > 0) {
+                            e = fe_add<F>(e, d);
                         }
-                    } else {
-#pragma unroll
-                        for (int t = 0; t <= D; t++) {
-                            if (t > 0) e = fe_add<F>(e, d);
-                            if (!(t == 1 && skip1)) p[t] = fe_mul<F>(p[t], e);
+                        if ((t == 1 && skip1) || (TOOM && t == 3 && !inf)) continue;
+                        if (WIDE && last) {
+                            uint32_t w[16];
+                            fe_mul_wide(w, p[t], e);
+                            accw_add16(accw_at(accw, t), w);
+                        } else {
+                            p[t] = fe_mul<F>(p[t], e);
                         }
                     }
                 }
@@ -126,12 +142,12 @@ __global__ void __launch_bounds__(kThreads)
                     if (len == 1) {
 #pragma unroll
                         for (int t = 0; t <= D; t++)
-                            if (!(t == 1 && skip1)) accw_add_hi(accw_at(accw, t), p[t]);
+                            if (!(t == 1 && skip1) && !(TOOM && t == 3 && !inf)) accw_add_hi(accw_at(accw, t), p[t]);
                     }
                 } else {
 #pragma unroll
                     for (int t = 0; t <= D; t++)
-                        if (!(t == 1 && skip1)) acc[t] = fe_add<F>(acc[t], p[t]);
+                        if (!(t == 1 && skip1) && !(TOOM && t == 3 && !inf)) acc[t] = fe_add<F>(acc[t], p[t]);
                 }
             }
         }
@@ -148,7 +164,7 @@ __global__ void __launch_bounds__(kThreads)
         for (int t = 0; t <= D; t++) acc[t] = accw_reduce<F>(accw_at(accw, t));
         __syncthreads();
     }
-    reduce_publish<F, D + 1>(acc, ra);
+    reduce_publish<F, D + 1, TOOM>(acc, ra);
 }
 
 }  // namespace
