@@ -13,6 +13,7 @@ PY
   tail -2 gpurun_out/r2_sop_bench_$name.err
 }
 run default ZK_X=1
+run notoom ZK_B200_SOP_TOOM=0
 run nogroup ZK_B200_SOP_GROUP=0
 run static ZK_B200_SOP_SCHED=static
 run narrow ZK_B200_SOP_WIDE=0

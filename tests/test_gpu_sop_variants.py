@@ -12,8 +12,9 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("env", [{"ZK_B200_SOP_WIDE": "1"}, {"ZK_B200_SOP_GROUP": "0", "ZK_B200_SOP_SCHED": "static"}, {"ZK_B200_SOP_FOLD_PIPE": "f64"}],
-                         ids=["deferred-reduction", "no-grouping-static-split", "fp64-folds"])
+@pytest.mark.parametrize("env", [{"ZK_B200_SOP_WIDE": "1"}, {"ZK_B200_SOP_GROUP": "0", "ZK_B200_SOP_SCHED": "static"}, {"ZK_B200_SOP_FOLD_PIPE": "f64"},
+                                  {"ZK_B200_SOP_TOOM": "0"}],
+                         ids=["deferred-reduction", "no-grouping-static-split", "fp64-folds", "points-0-to-3"])
 def test_sum_of_products_kernel_variant(env):
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", os.path.join(ROOT, "tests", "test_gpu_sop.py")],
                        capture_output=True, text=True, env=dict(os.environ, **env), timeout=900, cwd=ROOT)
