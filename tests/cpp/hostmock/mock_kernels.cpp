@@ -294,10 +294,12 @@ cudaError_t launch_generate(int field, Fe* out, uint64_t count, uint64_t seed, u
     }
     return cudaSuccess;
 }
-cudaError_t launch_interleave(const Fe* in, Fe* out, uint64_t local_len, unsigned world, cudaStream_t, int* launches) {
+cudaError_t launch_interleave(const Fe* in, Fe* out, uint64_t local_len, unsigned world, cudaStream_t, int* launches, unsigned batch) {
     ++*launches;
-    for (uint64_t q = 0; q < world; q++)
-        for (uint64_t j = 0; j < local_len; j++) out[j * world + q] = in[q * local_len + j];
+    const uint64_t per = local_len * world;
+    for (uint64_t b = 0; b < batch; b++)
+        for (uint64_t q = 0; q < world; q++)
+            for (uint64_t j = 0; j < local_len; j++) out[b * per + j * world + q] = in[b * per + q * local_len + j];
     return cudaSuccess;
 }
 cudaError_t launch_deinterleave(const Fe* in, Fe* out, uint64_t local_len, unsigned world, cudaStream_t, int* launches) {

@@ -166,15 +166,22 @@ static int prove_core(zk_ctx* ctx, zk_table* const* tables, unsigned m, unsigned
             CU(ctx, cudaMalloc((void**)&ctx->gather_buf, need * sizeof(Fe)));
             ctx->gather_cap = need;
         }
-        for (unsigned k = 0; k < m; k++) {
-            Fe* stage = ctx->gather_buf + (size_t)k * L * G;
-            Fe* full = ctx->gather_buf + (size_t)(m + k) * L * G;
-            int rc = nccl().AllGather(cur.t[k], stage, (size_t)L * 32, kNcclUint8, ctx->comm, ctx->stream);
-            if (rc != 0) return fail(ctx, ZK_ERR_NCCL, "allgather");
-            cudaError_t e = zk::launch_interleave(stage, full, L, (unsigned)G, ctx->stream, &ctx->launches);
-            if (e != cudaSuccess) return cuda_fail(ctx, e, "gather");
-            cur.t[k] = full;
+        // one NCCL group for the m all-gathers (a single fused launch) and one interleave launch for all tables:
+        // landing zones [k][q][j] and interleaved tables [k][j G + q] are stored back to back
+        Fe* const stage0 = ctx->gather_buf;
+        Fe* const full0 = ctx->gather_buf + (size_t)m * L * G;
+        const bool grouped = nccl().p2p_ok;
+        int rc = grouped ? nccl().GroupStart() : 0;
+        for (unsigned k = 0; k < m && rc == 0; k++)
+            rc = nccl().AllGather(cur.t[k], stage0 + (size_t)k * L * G, (size_t)L * 32, kNcclUint8, ctx->comm, ctx->stream);
+        if (grouped) {
+            const int rc_end = nccl().GroupEnd();
+            if (rc == 0) rc = rc_end;
         }
+        if (rc != 0) return fail(ctx, ZK_ERR_NCCL, "allgather");
+        cudaError_t e = zk::launch_interleave(stage0, full0, L, (unsigned)G, ctx->stream, &ctx->launches, m);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "gather");
+        for (unsigned k = 0; k < m; k++) cur.t[k] = full0 + (size_t)k * L * G;
         cur_len = L * G;
         sharded = false;
         return ZK_OK;

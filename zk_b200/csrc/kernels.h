@@ -154,8 +154,9 @@ cudaError_t launch_convert(int field, Fe* data, uint64_t n, bool to_mont, cudaSt
 cudaError_t launch_generate(int field, Fe* out, uint64_t count, uint64_t seed, uint64_t table_id, uint64_t first,
                             uint64_t stride, cudaStream_t stream, int* launches);
 // out[j*G + q] = in[q*L + j]: re-interleave the all-gathered residual shards (q-major) into global order
+// (`batch` tables stored back to back, in and out, in one launch)
 cudaError_t launch_interleave(const Fe* in, Fe* out, uint64_t local_len, unsigned world, cudaStream_t stream,
-                              int* launches);
+                              int* launches, unsigned batch = 1);
 // After the exact ncclSum all-reduce of the u64 lanes (one 32-bit limb per lane, written by the reducing
 // launch): carry-propagate the lane sums, reduce mod p, publish result + completion flag.
 cudaError_t launch_narrow(int field, const uint64_t* lanes, Fe* out_dev, Fe* out_host_devptr, int count,

@@ -96,11 +96,12 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
-__global__ void __launch_bounds__(kThreads) interleave_kernel(const Fe* in, Fe* out, uint64_t local_len, unsigned world) {
-    const uint64_t total = local_len * world, stride = (uint64_t)gridDim.x * kThreads;
+// `batch` tables back to back (in: [b][q][j], out: [b][j * world + q]) in one launch
+__global__ void __launch_bounds__(kThreads) interleave_kernel(const Fe* in, Fe* out, uint64_t local_len, unsigned world, unsigned batch) {
+    const uint64_t per = local_len * world, total = per * batch, stride = (uint64_t)gridDim.x * kThreads;
     for (uint64_t g = (uint64_t)blockIdx.x * kThreads + threadIdx.x; g < total; g += stride) {
-        uint64_t j = g / world, q = g % world;
-        st_fe(out + g, ld_fe(in + q * local_len + j));
+        const uint64_t b = g / per, r = g % per, j = r / world, q = r % world;
+        st_fe(out + g, ld_fe(in + b * per + q * local_len + j));
     }
 }
 
@@ -201,8 +202,8 @@ cudaError_t launch_generate(int field, Fe* out, uint64_t count, uint64_t seed, u
     return cudaGetLastError();
 }
 cudaError_t launch_interleave(const Fe* in, Fe* out, uint64_t local_len, unsigned world, cudaStream_t stream,
-                              int* launches) {
-    interleave_kernel<<<grid_1d(local_len * world), kThreads, 0, stream>>>(in, out, local_len, world);
+                              int* launches, unsigned batch) {
+    interleave_kernel<<<grid_1d(local_len * world * batch), kThreads, 0, stream>>>(in, out, local_len, world, batch);
     ++*launches;
     return cudaGetLastError();
 }
