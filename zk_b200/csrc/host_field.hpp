@@ -81,22 +81,35 @@ class Field {
         return r;
     }
     El neg(const El& a) const { return sub(zero(), a); }
-    // Montgomery product, word-serial (SOS with interleaved reduction)
+    // Montgomery product: coarsely integrated operand scanning on 4 x 64-bit limbs, branch free (it sits on the round loop's
+    // latency chain: challenge multiples, round-polynomial evaluation, transcript serialisation — a few dozen per round)
     El mul(const El& a, const El& b) const {
-        uint64_t t[9] = {0};
+        uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
         for (int i = 0; i < 4; i++) {
-            u128 c = 0;
-            for (int j = 0; j < 4; j++) { c += (u128)a.v[j] * b.v[i] + t[i + j]; t[i + j] = (uint64_t)c; c >>= 64; }
-            for (int k = i + 4; c && k < 9; k++) { c += t[k]; t[k] = (uint64_t)c; c >>= 64; }
+            const uint64_t bi = b.v[i];
+            u128 c = (u128)a.v[0] * bi + t0;
+            const uint64_t lo0 = (uint64_t)c;
+            c = (u128)a.v[1] * bi + t1 + (uint64_t)(c >> 64);
+            const uint64_t lo1 = (uint64_t)c;
+            c = (u128)a.v[2] * bi + t2 + (uint64_t)(c >> 64);
+            const uint64_t lo2 = (uint64_t)c;
+            c = (u128)a.v[3] * bi + t3 + (uint64_t)(c >> 64);
+            const uint64_t lo3 = (uint64_t)c;
+            const u128 top = (u128)t4 + (uint64_t)(c >> 64);  // < 2^65
+            const uint64_t m = lo0 * P.inv;
+            c = (u128)m * P.p[0] + lo0;                        // low word becomes 0
+            c = (u128)m * P.p[1] + lo1 + (uint64_t)(c >> 64);
+            t0 = (uint64_t)c;
+            c = (u128)m * P.p[2] + lo2 + (uint64_t)(c >> 64);
+            t1 = (uint64_t)c;
+            c = (u128)m * P.p[3] + lo3 + (uint64_t)(c >> 64);
+            t2 = (uint64_t)c;
+            const u128 hi = top + (uint64_t)(c >> 64);
+            t3 = (uint64_t)hi;
+            t4 = (uint64_t)(hi >> 64);
         }
-        for (int i = 0; i < 4; i++) {
-            uint64_t m = t[i] * P.inv;
-            u128 c = 0;
-            for (int j = 0; j < 4; j++) { c += (u128)m * P.p[j] + t[i + j]; t[i + j] = (uint64_t)c; c >>= 64; }
-            for (int k = i + 4; c && k < 9; k++) { c += t[k]; t[k] = (uint64_t)c; c >>= 64; }
-        }
-        El r; std::memcpy(r.v, t + 4, 32);
-        if (t[8] || geq_p(r.v)) sub_p(r.v);
+        El r{{t0, t1, t2, t3}};
+        if (t4 || geq_p(r.v)) sub_p(r.v);
         return r;
     }
     El from_canonical(const uint64_t c[4]) const {  // c < p
