@@ -7,13 +7,19 @@
 
 Workload (config.workload): BASELINE config 3 — degree-3 product sumcheck (3 factor tables, MAX_VAR_DEGREE = 3),
 `prove_partial`, BLS12-381 Fr, synthetic seeded tables.  N = 1: 2^26 entries per table (6 GiB, larger than L2).
-N > 1: weak scaling, 2^26 entries per GPU (2^(26+log2 N) total; `--log-n 30` gives BASELINE config 4 exactly),
-tables sharded by the last-bound variables, round polynomials all-reduced over NCCL.
+N > 1: weak scaling, 2^26 entries per GPU (2^(26+log2 N) total), tables sharded by the last-bound variables, the round
+sums all-reduced inside the reducing launch (peer mailboxes over NVLink; NCCL all-reduce as the fallback); the same line
+carries a `config4` record: BASELINE config 4 exactly (2^30 entries over the N GPUs).  N = 1: an `ntt` record, BASELINE
+config 5 (the fft crate's NTT / INTT, 2^16 .. 2^28 points, both fields).  Every proof and transform the line reports is
+compared with the CPU oracle's committed digest of the same seeded input (`proof_equals_cpu_oracle_golden`,
+`fft_equals_cpu_oracle_golden`).
 
 A step = one whole proof.  `value` = ALG_MULS / prove time with tables resident in HBM (tables are
 regenerated on the device between steps, outside the timed region, because prove consumes them);
 ALG_MULS(n,m,D) = ((D+1)(m-1)+m)(2^n-1)  (SURVEY.md 8d).  `e2e` = the same metric through
 zk_sumcheck_prove_host with HOST (pinned) tables: H2D of every table and D2H of the proof inside the timed region.
+`--impl reference`: the reference's CPU algorithm (the reference-shaped C port of oracle/, one core like the reference) on a
+bounded sample of the same workload, named in `config.sampled_log_n`.
 """
 from __future__ import annotations
 
