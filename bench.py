@@ -559,6 +559,19 @@ def run_ours(args):
                 # issue rates, whichever is longer, over the measured launch time
                 "pipe_frac": max(wide_per_s / mb["imad_wide_per_s"], dfma_per_s / mb["dfma_per_s"]),
                 "whole_prove": {"alg_bytes": alg_bytes(n, m) / world, "gbs": alg_bytes(n, m) / world / (ms_per_step * 1e-3) / 1e9}}
+    # the second kernel of the step: round 0 (no fold): reads every table once, multiplies only — bound by the integer-multiply pipe
+    if len(main_round_ms) > 1 and m >= 2:
+        r0_s = main_round_ms[0] * 1e-3
+        r0_items = local_n0 // 2
+        if m == 3 and d == 3:
+            r0_wide = 3 * 112 + 4 * 64  # Toom point set: 3 reduced products + 4 unreduced last products
+        else:
+            r0_wide = (m - 2) * (d + 1) * 112 + (d + 1) * 64
+        roofline["round0"] = {"kernel": f"round_kernel<Fr381,{d},FOLD=false> (round 0, m={m})", "launch_ms": main_round_ms[0],
+                              "bound": "IMAD.WIDE.U32 issue rate", "imad_wide_per_item": r0_wide,
+                              "achieved_imad_wide_per_s": r0_wide * r0_items / r0_s, "peak_imad_wide_per_s": mb["imad_wide_per_s"],
+                              "frac": r0_wide * r0_items / r0_s / mb["imad_wide_per_s"],
+                              "hbm_gbs": 32 * m * local_n0 / r0_s / 1e9, "hbm_frac": 32 * m * local_n0 / r0_s / 1e9 / peaks["hbm_gbs"]}
 
     # ---- CPU baseline beside it (bounded sample, rank 0, N = 1 only) ----------------------------------------------
     cpu = None
