@@ -155,11 +155,7 @@ struct WarpChunks {  // 32-bit chunk ids: tables of up to 2^37 items
 // F64 (only with FOLD): the folds run on the FP64 pipe (field_f64.cuh: exact DFMA dot products against 16 host-made
 // multiples of the challenge, one Montgomery row) instead of fe_mul_fixed's 76 wide multiplies.
 template <class F, int D, bool FOLD, bool TOOM = false, bool F64 = false, bool DYN = false>
-#ifdef ZK_RK_MAXNREG  // tuning builds: an exact register cap instead of a resident-block count (with ZK_THREADS, see reduce.cuh)
-__global__ void __maxnreg__(ZK_RK_MAXNREG)
-#else
 __global__ void __launch_bounds__(kThreads, (D <= 1) ? (FOLD ? ZK_RK_MINBLOCKS_D1 : ZK_RK_MINBLOCKS_D1 - 1) : (D == 2 ? ZK_RK_MINBLOCKS_D2 : ZK_RK_MINBLOCKS_D3))
-#endif
     round_kernel(TablePtrs tabs, int m, uint64_t q, uint64_t hoff, const __grid_constant__ FixedMul rtab,
                  const __grid_constant__ FixedMulF64Sel rtab64, ReduceArgs ra) {
     static_assert(!TOOM || D == 3, "the Toom point set is wired for cubics");

@@ -14,13 +14,9 @@
 namespace zk {
 namespace {
 
-#ifndef ZK_THREADS
-#define ZK_THREADS 128
-#endif
-constexpr int kThreads = ZK_THREADS;
+constexpr int kThreads = 128;
 
 constexpr int kWarps = kThreads / 32;
-constexpr int kWarpsPow2 = kWarps <= 1 ? 1 : kWarps <= 2 ? 2 : kWarps <= 4 ? 4 : kWarps <= 8 ? 8 : kWarps <= 16 ? 16 : 32;  // xor-shuffle width covering kWarps lanes
 
 __device__ __forceinline__ Fe ld_fe_cg(const Fe* p) {  // L2-coherent load (other blocks' partials)
     Fe r;
@@ -237,7 +233,7 @@ __device__ __forceinline__ void reduce_publish(Fe* acc, const ReduceArgs& ra) {
 #pragma unroll 1
         for (int t = 0; t < NP; t++) {
             Fe v = (lane < kWarps) ? sh[t][lane] : fe_zero<F>();
-            v = warp_sum<F>(v, kWarpsPow2);
+            v = warp_sum<F>(v, kWarps);
             if (lane == 0) st_fe(ra.block_partials + (size_t)blockIdx.x * NP + t, v);
         }
     }
@@ -260,7 +256,7 @@ __device__ __forceinline__ void reduce_publish(Fe* acc, const ReduceArgs& ra) {
         __syncthreads();
         if (warp == 0) {
             Fe w = (lane < kWarps) ? sh[0][lane] : fe_zero<F>();
-            w = warp_sum<F>(w, kWarpsPow2);
+            w = warp_sum<F>(w, kWarps);
             if (lane == 0) s_fin[t] = w;
         }
     }
