@@ -311,6 +311,7 @@ void zk_ctx_destroy(zk_ctx* c) {
     for (auto* pl : c->ntt_plans) zk::ntt_plan_destroy(pl);
     cudaFree(c->gather_buf);
     cudaFree(c->eval_buf);
+    cudaFree(c->ntt_host_buf);
     for (auto ev : c->events) cudaEventDestroy(ev);
     cudaFree(c->scratch.block_partials);
     cudaFree(c->scratch.ticket);

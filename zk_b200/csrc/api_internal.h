@@ -70,6 +70,8 @@ struct zk_ctx {
     unsigned cur_seq = 0;                 // sequence number of the reduction in flight
     Fe* gather_buf = nullptr;             // persistent staging for the residual all-gather (grow-only)
     size_t gather_cap = 0;                // elements
+    Fe* ntt_host_buf = nullptr;           // device landing buffer of zk_ntt_host, kept between calls
+    size_t ntt_host_cap = 0;              // elements
     Fe* eval_buf = nullptr;               // persistent half-size work table of zk_mle_evaluate (grow-only)
     size_t eval_cap = 0;                  // elements
     std::vector<cudaStream_t> copy_streams;  // extra H2D streams of zk_sumcheck_prove_host (lazily created)

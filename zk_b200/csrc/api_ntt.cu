@@ -46,12 +46,24 @@ int zk_ntt(zk_ctx* ctx, zk_table* inout, int inverse) {
 int zk_ntt_host(zk_ctx* ctx, int field, uint64_t* data, uint64_t len, int inverse) {
     if (!ctx || !data || !valid_field(field)) return fail(ctx, ZK_ERR_INVALID_ARG);
     if (len == 0 || (len & (len - 1))) return fail(ctx, ZK_ERR_NOT_POW2);
-    zk_table* t = nullptr;
-    int st = zk_table_upload(ctx, field, data, len, log2_exact(len), &t);
-    if (st != ZK_OK) return st;
-    st = zk_ntt(ctx, t, inverse);
-    if (st == ZK_OK) st = zk_table_download(ctx, t, data);
-    zk_table_free(t);
+    if (ctx->world > 1) return fail(ctx, ZK_ERR_UNSUPPORTED, "NTT on a sharded context (replicas only)");
+    CU(ctx, cudaSetDevice(ctx->device));
+    // The device landing buffer stays with the context between calls (grow-only, like zk_sumcheck_prove_host's): a
+    // cudaMalloc + cudaFree of the whole vector per call costs milliseconds and a device-wide synchronisation each.
+    if (ctx->ntt_host_cap != len) {  // exact size: zk_ntt then swaps it with the plan's scratch instead of copying back
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->ntt_host_buf);
+        ctx->ntt_host_buf = nullptr;
+        ctx->ntt_host_cap = 0;
+        cudaError_t ea = cudaMalloc((void**)&ctx->ntt_host_buf, (size_t)len * sizeof(Fe));
+        if (ea != cudaSuccess) { cudaGetLastError(); return cuda_fail(ctx, ea, "cudaMalloc(ntt vector)"); }
+        ctx->ntt_host_cap = (size_t)len;
+    }
+    zk_table t{ctx, field, log2_exact(len), len, ctx->ntt_host_buf, (size_t)len};
+    CU(ctx, cudaMemcpyAsync(t.data, data, (size_t)len * 32, cudaMemcpyHostToDevice, ctx->stream));
+    int st = zk_ntt(ctx, &t, inverse);
+    ctx->ntt_host_buf = t.data;  // zk_ntt may have exchanged the buffer with its plan's scratch
+    if (st == ZK_OK) st = zk_table_download(ctx, &t, data);
     return st;
 }
 
