@@ -351,3 +351,31 @@ def test_square_of_one_polynomial_vs_oracle(zk, ctx, cref):
     assert lib.zk_product_sum(ctx.h, arr, 2, s.ctypes.data) == 0
     assert (s == cref.product_sum(0, refs[:2], n)).all()
     assert (f2.evaluation_slice_mont() == refs[0]).all()  # untouched by the refused calls
+
+
+def test_randomised_shapes_vs_c_oracle(zk, ctx, cref):
+    """A seeded sweep over (field, n, m, D) — 1..8 factors, MAX_VAR_DEGREE 1..5 (5: the generic one-point-per-launch path),
+    1..15 variables — so that every kernel the dispatcher can pick for a round (streaming, latency kernel with 2m <= 8
+    lanes, the ragged single chunk of tables under 32 items, Toom / plain point sets, derived and summed S(1)) meets the
+    oracle on shapes nobody chose by hand.  Claims are true for even cases and false for odd ones."""
+    import random
+
+    rng = random.Random(20261018)
+    for case in range(40):
+        fid = rng.randrange(2)
+        m = rng.choice([1, 2, 3, 3, 4, 5, 8])
+        d = rng.choice([1, 2, 3, 3, 4, 5])
+        n = rng.randrange(1, 16 if m <= 4 else 12)
+        seed = rng.randrange(1 << 40)
+        refs = [cref.gen_table(fid, seed, k, n) for k in range(m)]
+        claim = cref.product_sum(fid, refs, n)
+        if case & 1:
+            claim = cref.ints_to_mont(fid, [rng.randrange(1 << 200)])[0]
+        rp, ch, fin = cref.prove(fid, refs, n, d, claim, False, fast=True)
+        pp = zk.ProductPoly.new(gpu_tables(zk, fid, seed, n, m))
+        prover = zk.SumcheckProver(d)
+        proof, chs = prover.prove_partial(pp, cref.mont_to_ints(fid, claim.reshape(1, 4))[0])
+        tag = (case, fid, n, m, d)
+        assert (proof._round_polys_mont == rp).all(), tag
+        assert chs == cref.mont_to_ints(fid, ch), tag
+        assert prover.final_evals == cref.mont_to_ints(fid, fin), tag
