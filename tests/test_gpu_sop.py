@@ -157,3 +157,39 @@ def test_prove_and_verify_with_the_initial_absorb(zk, ctx):
         zk.SumcheckVerifier.verify(keep, zk.SumcheckProof.from_values(0, proof.sum, proof.round_polys[:-1]))
     with pytest.raises(zk.ZkError, match="claimed_sum != p\\(0\\) \\+ p\\(1\\)"):
         zk.SumcheckVerifier.verify(keep, zk.SumcheckProof.from_values(0, proof.sum + 1, proof.round_polys))
+
+
+def test_randomised_term_structures_vs_c_oracle(zk, ctx, cref):
+    """A seeded sweep over term structures: 1..6 tables, 1..5 terms of 1..4 factors (repeats allowed, every table used),
+    MAX_VAR_DEGREE 1..4 at, above and below the longest term, 2..13 variables — so that the launcher's common-factor
+    extraction (terms that differ in one table), the Toom point set (degree 3, no term longer than three), the latency
+    kernel (at most four tables) and the streaming kernel all meet the oracle on shapes nobody chose by hand."""
+    import random
+
+    rng = random.Random(4242)
+    for case in range(30):
+        fid = rng.randrange(2)
+        nt = rng.randrange(1, 7)
+        n_terms = rng.randrange(1, 6)
+        terms = [[rng.randrange(nt) for _ in range(rng.randrange(1, 5))] for _ in range(n_terms)]
+        if case % 3 == 0 and nt >= 3:  # plant a pair that differs in exactly one table: x.a + x.b
+            terms[0] = [0, 1]
+            terms.append([0, 2])
+        for k in range(nt):  # every table appears somewhere (its fold is part of the proof's final evaluations either way)
+            if not any(k in t for t in terms):
+                terms[rng.randrange(len(terms))][0:0] = [k] if len(terms[0]) < 4 else []
+        terms = [t[:4] for t in terms][:8]
+        d = rng.choice([1, 2, 3, 3, 4])
+        n = rng.randrange(2, 14)
+        seed = rng.randrange(1 << 40)
+        sp = gpu_sop(zk, fid, seed, n, nt, terms)
+        refs = [cref.gen_table(fid, seed, 20 + k, n) for k in range(nt)]
+        rsum = cref.sop_sum(fid, refs, terms, n)
+        assert (sp.sum_mont() == rsum).all(), (case, terms)
+        rp, ch, fin = cref.prove_sop(fid, refs, terms, n, d, rsum)
+        prover = zk.SumcheckProver(d)
+        proof, gch = prover.prove_partial(sp, zk.from_mont(fid, rsum)[0])
+        tag = (case, fid, n, nt, terms, d)
+        assert first_mismatch(proof._round_polys_mont, rp) is None, (tag, first_mismatch(proof._round_polys_mont, rp))
+        assert gch == cref.mont_to_ints(fid, ch), tag
+        assert prover.final_evals == cref.mont_to_ints(fid, fin), tag

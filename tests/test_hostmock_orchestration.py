@@ -105,7 +105,7 @@ def test_gpu_suite_files_replayed_under_the_host_mock():
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", files[1]], capture_output=True, text=True,
                        env=dict(env, ZK_B200_SOP_WIDE="1"), timeout=900, cwd=ROOT)
     tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
-    assert r.returncode == 0 and "14 passed" in tail, r.stdout[-3000:] + r.stderr[-2000:]
+    assert r.returncode == 0 and " passed" in tail and "failed" not in tail and int(tail.split(" passed")[0].split()[-1]) >= 15, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_cpp_mirror_runs_under_the_host_mock():
