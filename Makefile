@@ -6,7 +6,7 @@ SRC := zk_b200/csrc
 OBJDIR := build
 OBJS := $(OBJDIR)/api.o $(OBJDIR)/api_sumcheck.o $(OBJDIR)/api_ntt.o $(OBJDIR)/kernels_sumcheck.o $(OBJDIR)/kernels_sop.o $(OBJDIR)/kernels_mle.o $(OBJDIR)/kernels_ntt.o $(OBJDIR)/kernels_ntt_sharded.o $(OBJDIR)/microbench.o \
         $(OBJDIR)/keccak_avx512.o
-HDRS := $(SRC)/field.cuh $(SRC)/field_f64.cuh $(SRC)/reduce.cuh $(SRC)/accw.cuh $(SRC)/sop_kernel.cuh $(SRC)/ntt_sharded_kernels.cuh $(SRC)/kernels.h $(SRC)/api_internal.h $(SRC)/host_field.hpp $(SRC)/keccak.hpp include/zk_b200.h
+HDRS := $(SRC)/field.cuh $(SRC)/field_f64.cuh $(SRC)/fold_imma.cuh $(SRC)/reduce.cuh $(SRC)/accw.cuh $(SRC)/sop_kernel.cuh $(SRC)/ntt_sharded_kernels.cuh $(SRC)/kernels.h $(SRC)/api_internal.h $(SRC)/host_field.hpp $(SRC)/keccak.hpp include/zk_b200.h
 
 all: zk_b200/libzk_b200.so
 

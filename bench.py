@@ -527,7 +527,8 @@ def run_ours(args):
     # Instructions actually issued per item of the fused step.  Product multiplications (field.cuh): an intermediate
     # product is 112 IMAD.WIDE.U32, the last product of a term 64 (unreduced); the cubic/3-factor case carries its
     # terms at the Toom points (3 intermediate products instead of 4).  Folds: with two or more factors they run on
-    # the FP64 pipe (field_f64.cuh: 128 DFMA + 6 IMAD.WIDE each), a single table folds on the integer pipe (76).
+    # the FP64 pipe (field_f64.cuh: 128 DFMA + 6 IMAD.WIDE each), a single table folds on the integer pipe (76);
+    # the headline shape folds on the INT8 tensor path (below).
     # Rounds >= 1 with D >= m derive S(1) from the previous round polynomial: one unreduced product less per item.
     last_terms = d if d >= m else d + 1
     if m == 1:
@@ -536,10 +537,21 @@ def run_ours(args):
         prod_wide = 3 * 112 + last_terms * 64
     else:
         prod_wide = (m - 2) * (d + 1) * 112 + last_terms * 64
-    fold_pipe = os.environ.get("ZK_B200_FOLD_PIPE", "f64" if m >= 2 else "int")[0]
-    fold_wide, fold_dfma = (6, 128) if fold_pipe == "f" else (76, 0)
+    # The degree-3, three-factor step folds on the INT8 tensor path (fold_imma.cuh: 8 IMMA.16832.U8.U8 per WARP and fold,
+    # 6 IMAD.WIDE per thread for the Montgomery row); ZK_B200_FOLD_PIPE selects another pipe.
+    tensor_ok = m == 3 and d == 3
+    fold_pipe = os.environ.get("ZK_B200_FOLD_PIPE", "imma2" if tensor_ok else ("f64" if m >= 2 else "int"))
+    if fold_pipe.startswith("im") and not tensor_ok:
+        fold_pipe = "f64" if m >= 2 else "int"
+    if fold_pipe.startswith("im"):
+        fold_wide, fold_dfma, fold_imma = 6, 0, 8
+    elif fold_pipe.startswith("f"):
+        fold_wide, fold_dfma, fold_imma = 6, 128, 0
+    else:
+        fold_wide, fold_dfma, fold_imma = 76, 0, 0
     wide_per_item = 2 * m * fold_wide + prod_wide
     dfma_per_item = 2 * m * fold_dfma
+    imma_per_warp_item = 2 * m * fold_imma  # one warp = 32 items
     items = local_n0 // 4
     wide_per_s = wide_per_item * items / fused_s
     dfma_per_s = dfma_per_item * items / fused_s
@@ -555,6 +567,10 @@ def run_ours(args):
                 "fp64_pipe": {"bound": "DFMA issue rate (the folds: exact FP64 dot products against multiples of the challenge)",
                               "dfma_per_item": dfma_per_item, "achieved_dfma_per_s": dfma_per_s, "peak_dfma_per_s": mb["dfma_per_s"],
                               "frac": dfma_per_s / mb["dfma_per_s"], "standalone_fe_mul_fixed_per_s": mb["fe_mul_fixed_per_s"]},
+                "fold_pipe": fold_pipe,
+                "tensor_pipe": {"instruction": "IMMA.16832.U8.U8 (mma.sync.m16n8k32.u8.u8.s32: the bytes of h - l against a 32 x 32 byte table of the challenge's multiples, exact s32 sums)",
+                                "imma_per_warp_of_32_items": imma_per_warp_item, "achieved_imma_per_s": imma_per_warp_item * (items / 32) / fused_s,
+                                "peak_imma_per_s": 1.40e11, "peak_source": "tools/imma_fold_probe.cu on this pool's B200 (profiles/r02_imma_fold_experiment.txt)"},
                 # both pipes run concurrently: the time the two instruction streams would need at their measured peak
                 # issue rates, whichever is longer, over the measured launch time
                 "pipe_frac": max(wide_per_s / mb["imad_wide_per_s"], dfma_per_s / mb["dfma_per_s"]),
@@ -591,7 +607,7 @@ def run_ours(args):
     line = {
         "metric": "sumcheck_prove_field_mul_per_s", "value": value, "unit": "field-mul/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs; IMAD.WIDE products, exact FP64 folds)", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs; IMAD.WIDE products, folds as exact INT8 tensor-core / FP64 dot products)", "data": "synthetic",
         "config": workload_config(n, m, d, world), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "cpu_baseline": cpu, "prove_ms": ms_per_step, "proof_keccak": proof_digest, "verified": verified,
         "proof_equals_cpu_oracle_golden": golden_parity, "golden_oracle": res["golden_oracle"],

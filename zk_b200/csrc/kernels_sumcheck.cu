@@ -18,6 +18,7 @@
 // D+1 evaluations to device memory and to mapped pinned host memory.
 #include "kernels.h"
 #include "field_f64.cuh"
+#include "fold_imma.cuh"
 #include "reduce.cuh"
 #include "accw.cuh"
 #include "host_field.hpp"
@@ -37,6 +38,9 @@ namespace {
 #ifndef ZK_RK_MINBLOCKS_D3
 #define ZK_RK_MINBLOCKS_D3 4
 #endif
+#ifndef ZK_RK_MINBLOCKS_IMMA
+#define ZK_RK_MINBLOCKS_IMMA 4  // 5 fits (96 registers without the prefetch) and measured slower: 2.50 against 2.36 ms
+#endif
 
 // One hypercube item, factor k of m: lo / hi are the pair values of this factor for the item (after the
 // optional fold).  Term t of the round polynomial is prod_k e_k(t), e_k(0) = lo_k, e_k(1) = hi_k,
@@ -51,7 +55,8 @@ namespace {
 // instead of (0, 1, 2, 3).  After the second factor the running product is a quadratic, fixed by three
 // values, so its value at -1 is 2(A(0) + A(inf)) - A(1): one multiplication less per item (7 instead of 8).
 // The four sums are mapped back to S(0..3) by exact field arithmetic in the last block (toom_to_evals).
-template <class F, int D, bool TOOM>
+// NO1 (with skip1 always on): the accumulator of t = 1 does not exist; the later points move one slot down.
+template <class F, int D, bool TOOM, bool NO1 = false>
 __device__ __forceinline__ void item_terms(int k, bool last, bool skip1, Fe lo, Fe hi, Fe* pr, const Accw& accw) {
     if (TOOM) {  // pr[0..3] live at t = 0, 1, -1, inf ; m == 3
         const Fe d = fe_sub<F>(hi, lo);
@@ -67,8 +72,8 @@ __device__ __forceinline__ void item_terms(int k, bool last, bool skip1, Fe lo, 
             uint32_t w[16];
             fe_mul_wide(w, lo, pr[0]); accw_add16(accw, w);
             if (!skip1) { fe_mul_wide(w, hi, pr[1]); accw_add16(accw_at(accw, 1), w); }
-            fe_mul_wide(w, fe_sub<F>(lo, d), pr[2]); accw_add16(accw_at(accw, 2), w);
-            fe_mul_wide(w, d, pr[3]); accw_add16(accw_at(accw, 3), w);
+            fe_mul_wide(w, fe_sub<F>(lo, d), pr[2]); accw_add16(accw_at(accw, NO1 ? 1 : 2), w);
+            fe_mul_wide(w, d, pr[3]); accw_add16(accw_at(accw, NO1 ? 2 : 3), w);
         }
     } else if (k == 0) {
         pr[0] = lo;
@@ -152,27 +157,59 @@ struct WarpChunks {  // 32-bit chunk ids: tables of up to 2^37 items
 };
 
 // ---- the round kernel -----------------------------------------------------------------------------------------
-// F64 (only with FOLD): the folds run on the FP64 pipe (field_f64.cuh: exact DFMA dot products against 16 host-made
-// multiples of the challenge, one Montgomery row) instead of fe_mul_fixed's 76 wide multiplies.
-template <class F, int D, bool FOLD, bool TOOM = false, bool F64 = false, bool DYN = false>
-__global__ void __launch_bounds__(kThreads, (D <= 1) ? (FOLD ? ZK_RK_MINBLOCKS_D1 : ZK_RK_MINBLOCKS_D1 - 1) : (D == 2 ? ZK_RK_MINBLOCKS_D2 : ZK_RK_MINBLOCKS_D3))
+// FP (only with FOLD) = the pipe that folds.  0: the integer pipe (fe_mul_fixed's 76 wide multiplies).  1: the FP64 pipe
+// (field_f64.cuh: exact DFMA dot products against 16 host-made multiples of the challenge, one Montgomery row).
+// 2 / 3: the INT8 tensor path (fold_imma.cuh: 8 IMMA per warp and fold on the bytes of h - l against a 32 x 32 byte table of
+// the challenge's multiples, one Montgomery row; 3 stages the two folds of an item together).  The table travels in the
+// bytes of rtab64.t[0]; the per-warp staging area follows the wide accumulators in shared memory.  q must be a multiple
+// of 32 (every lane of a warp owns an item: mma.sync).
+template <class F, int D, bool FOLD, bool TOOM = false, int FP = 0, bool DYN = false>
+__global__ void __launch_bounds__(kThreads, (D <= 1) ? (FOLD ? ZK_RK_MINBLOCKS_D1 : ZK_RK_MINBLOCKS_D1 - 1) : (D == 2 ? ZK_RK_MINBLOCKS_D2 : (FP >= 2 ? ZK_RK_MINBLOCKS_IMMA : ZK_RK_MINBLOCKS_D3)))
     round_kernel(TablePtrs tabs, int m, uint64_t q, uint64_t hoff, const __grid_constant__ FixedMul rtab,
                  const __grid_constant__ FixedMulF64Sel rtab64, ReduceArgs ra) {
     static_assert(!TOOM || D == 3, "the Toom point set is wired for cubics");
-    static_assert(!F64 || FOLD, "the FP64 variant only changes the folds");
-    extern __shared__ uint4 accw_all[];  // accw_bytes(D+1)
+    static_assert(FP == 0 || FOLD, "the fold-pipe variants only change the folds");
+    constexpr bool F64 = FP == 1, IMMA = FP >= 2;
+    constexpr int NF = FP == 3 ? 2 : 1;
+    // the tensor-path variants run with the claim known (skip1): no accumulator for t = 1 (8.7 KB of shared memory less)
+    constexpr int NPA = IMMA ? D : D + 1;
+    extern __shared__ uint4 accw_all[];  // accw_bytes(NPA) [+ kWarps * NF * kImmaStageBytes]
     __shared__ Fe* s_tab[kMaxFactors];
     if (threadIdx.x < kMaxFactors) s_tab[threadIdx.x] = tabs.t[threadIdx.x];
-    accw_zero(accw_all, D + 1);
+    accw_zero(accw_all, NPA);
     __syncthreads();
-    const Accw accw = accw_base(accw_all, D + 1);
+    const Accw accw = accw_base(accw_all, NPA);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ImmaTab itab{};
+    unsigned char* stage = nullptr;
+    if constexpr (IMMA) {
+        static_assert(sizeof(FixedMulI8) <= sizeof(FixedMulF64), "the byte table travels in the FP64 table's slot");
+        itab = imma_tab_load(reinterpret_cast<const FixedMulI8&>(rtab64.t[0]), lane);
+        stage = reinterpret_cast<unsigned char*>(accw_all) + accw_bytes(NPA) + (size_t)warp * NF * kImmaStageBytes;
+    }
+    auto fold2 = [&](Fe& lo, Fe& hi, const Fe& x0, const Fe& x1, const Fe& x2, const Fe& x3, int ksel) {
+        if constexpr (IMMA) {
+            if constexpr (NF == 2) {
+                Fe o[2];
+                const Fe l2[2] = {x0, x1}, h2[2] = {x2, x3};
+                fe_fold_imma_n<F, 2>(o, l2, h2, itab, stage, lane);
+                lo = o[0];
+                hi = o[1];
+            } else {
+                lo = fe_fold_imma<F>(x0, x2, itab, stage, lane);
+                hi = fe_fold_imma<F>(x1, x3, itab, stage, lane);
+            }
+        } else {
+            fold_pair<F, F64>(lo, hi, x0, x1, x2, x3, rtab, rtab64.t[ksel]);
+        }
+    };
     WarpChunks<DYN> wc(warp);
     // Software pipelining of the global loads.  Round 0 (no fold) keeps the pair of the next (item, factor) in
     // flight while this one is multiplied.  The fused kernel issues the four loads of the next (item, factor)
     // right AFTER this factor's folds (when x0..x3 are dead) so they land during the product multiplications
     // (-4 % at D = 3; at D <= 2 the register budget of the higher-occupancy variants makes it a loss).
-    constexpr bool kFoldPrefetch = FOLD && D >= 3;
+    // (a tensor-path build with five resident blocks has no registers for the prefetched quadruple)
+    constexpr bool kFoldPrefetch = FOLD && D >= 3 && (!IMMA || ZK_RK_MINBLOCKS_IMMA <= 4);
     Fe n0, n1, n2, n3;
     if ((uint64_t)wc.c * 32 + lane < q) {
         const uint64_t j0 = (uint64_t)wc.c * 32 + lane;
@@ -206,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? (FOLD ? ZK_RK_MINBLOCKS_D
                 Fe* NT = s_tab[more_k ? k + 1 : 0];
                 if (FOLD) {  // T has 4q entries: fold (j, j+2q) and (j+q, j+3q) at r, write back to j and j+q
                     if (kFoldPrefetch) {
-                        fold_pair<F, F64>(lo, hi, n0, n1, n2, n3, rtab, rtab64.t[ksel]);
+                        fold2(lo, hi, n0, n1, n2, n3, ksel);
                         st_fe(T + j, lo);
                         st_fe(T + j + q, hi);
                         if (nok) {
@@ -216,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? (FOLD ? ZK_RK_MINBLOCKS_D
                     } else {
                         Fe x0 = ld_fe_stream(T + j), x2 = ld_fe_stream(T + j + 2 * q);
                         Fe x1 = ld_fe_stream(T + j + q), x3 = ld_fe_stream(T + j + 3 * q);
-                        fold_pair<F, F64>(lo, hi, x0, x1, x2, x3, rtab, rtab64.t[ksel]);
+                        fold2(lo, hi, x0, x1, x2, x3, ksel);
                         st_fe(T + j, lo);
                         st_fe(T + j + q, hi);
                     }
@@ -228,14 +265,17 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? (FOLD ? ZK_RK_MINBLOCKS_D
                         n1 = ld_fe_stream(NT + nj + hoff);
                     }
                 }
-                item_terms<F, D, TOOM>(k, k == m - 1, FOLD && ra.skip1 != 0, lo, hi, pr, accw);
+                item_terms<F, D, TOOM, IMMA>(k, k == m - 1, IMMA || (FOLD && ra.skip1 != 0), lo, hi, pr, accw);
             }
         }
         wc.advance();
     }
     Fe acc[D + 1];
 #pragma unroll 1
-    for (int t = 0; t <= D; t++) acc[t] = accw_reduce<F>(accw_at(accw, t));
+    for (int t = 0; t <= D; t++) {
+        if (IMMA && t == 1) acc[t] = fe_zero<F>();  // S(1) comes from the claim (reduce_publish)
+        else acc[t] = accw_reduce<F>(accw_at(accw, IMMA && t > 1 ? t - 1 : t));
+    }
     __syncthreads();
     reduce_publish<F, D + 1, TOOM>(acc, ra);
 }
@@ -304,22 +344,49 @@ Fe small_constant(unsigned t);  // Montgomery form of small integer t (host side
 inline bool fold_on_f64(int m) {
     static const int forced = [] {
         const char* e = std::getenv("ZK_B200_FOLD_PIPE");
-        return !e ? -1 : (e[0] == 'f' ? 1 : 0);
+        return !e ? -1 : (e[0] == 'i' && e[1] == 'n' ? 0 : 1);
     }();
     return forced >= 0 ? forced == 1 : m >= 2;
 }
+// The INT8 tensor path (fold_imma.cuh) for the degree-3, three-factor fused step with the claim known (the prover's
+// rounds): measured 2.36 ms against 2.44 ms (FP64 folds) for the first fused step of the 2^26 proof, bit-exact.
+// ZK_B200_FOLD_PIPE=imma2 (default: the two folds of an item staged together) | imma (one at a time: 2.52 ms) |
+// f64 | int (the other pipes).  Returns the kernel's FP parameter, 0 = off.
+inline int fold_on_imma() {
+    static const int mode = [] {
+        const char* e = std::getenv("ZK_B200_FOLD_PIPE");
+        if (!e) return 3;
+        if (e[0] != 'i' || e[1] != 'm') return 0;
+        return e[4] == '2' ? 3 : 2;
+    }();
+    return mode;
+}
+// host: the byte table of the challenge's multiples in IMMA fragment order, carried in the first FP64 table's bytes
+template <class F>
+FixedMulF64Sel make_fixed_i8(const Fe& r) {
+    static_assert(sizeof(FixedMulI8) <= sizeof(FixedMulF64), "the byte table travels in the FP64 table's slot");
+    host::Field HF(F::ID);
+    host::El rm;
+    std::memcpy(rm.v, r.v, 32);
+    FixedMulI8 t8;
+    fixed_mul_table_i8(HF, rm, &t8);
+    FixedMulF64Sel t{};
+    std::memcpy(&t.t[0], &t8, sizeof(t8));
+    return t;
+}
 
-template <class F, int D, bool FOLD, bool TOOM, bool F64, bool DYN>
+template <class F, int D, bool FOLD, bool TOOM, int FP, bool DYN>
 cudaError_t do_round_v(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st, const Fe* claim, uint64_t hoff) {
-    const FixedMul tab = (FOLD && !F64) ? make_fixed<F>(r) : FixedMul{};
-    const FixedMulF64Sel tab64 = F64 ? make_fixed_f64<F>(r) : FixedMulF64Sel{};
-    constexpr size_t smem = accw_bytes(D + 1);
+    constexpr bool F64 = FP == 1, IMMA = FP >= 2;
+    const FixedMul tab = (FOLD && FP == 0) ? make_fixed<F>(r) : FixedMul{};
+    const FixedMulF64Sel tab64 = F64 ? make_fixed_f64<F>(r) : (IMMA ? make_fixed_i8<F>(r) : FixedMulF64Sel{});
+    constexpr size_t smem = IMMA ? accw_bytes(D) + (size_t)kWarps * (FP == 3 ? 2 : 1) * kImmaStageBytes : accw_bytes(D + 1);
     static PerDeviceCache cache;
     const int bpsm = per_device(cache, [] {
-        cudaError_t e = cudaFuncSetAttribute(round_kernel<F, D, FOLD, TOOM, F64, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(round_kernel<F, D, FOLD, TOOM, FP, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return -(int)e;
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<F, D, FOLD, TOOM, F64, DYN>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<F, D, FOLD, TOOM, FP, DYN>, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
         return nb;
     });
     if (bpsm <= 0) return (cudaError_t)(-bpsm);
@@ -329,12 +396,17 @@ cudaError_t do_round_v(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, co
         ra.skip1 = 1;
         ra.claim = *claim;
     }
-    round_kernel<F, D, FOLD, TOOM, F64, DYN><<<grid, kThreads, smem, st>>>(tabs, m, q, hoff ? hoff : q, tab, tab64, ra);
+    round_kernel<F, D, FOLD, TOOM, FP, DYN><<<grid, kThreads, smem, st>>>(tabs, m, q, hoff ? hoff : q, tab, tab64, ra);
     return cudaGetLastError();
 }
 template <class F, int D, bool FOLD, bool TOOM = false>
 cudaError_t do_round(const TablePtrs& tabs, int m, uint64_t q, const Fe& r, const ReduceScratch& s, cudaStream_t st, const Fe* claim, uint64_t hoff) {
     const bool dyn = m >= 2 && dynamic_chunks();
+    if constexpr (FOLD && D == 3 && TOOM) {
+        const int imma = fold_on_imma();
+        if (imma && dyn && q % 32 == 0 && claim)
+            return imma == 3 ? do_round_v<F, D, FOLD, TOOM, 3, true>(tabs, m, q, r, s, st, claim, hoff) : do_round_v<F, D, FOLD, TOOM, 2, true>(tabs, m, q, r, s, st, claim, hoff);
+    }
     if (FOLD && fold_on_f64(m))
         return dyn ? do_round_v<F, D, FOLD, TOOM, FOLD, true>(tabs, m, q, r, s, st, claim, hoff) : do_round_v<F, D, FOLD, TOOM, FOLD, false>(tabs, m, q, r, s, st, claim, hoff);
     return dyn ? do_round_v<F, D, FOLD, TOOM, false, true>(tabs, m, q, r, s, st, claim, hoff) : do_round_v<F, D, FOLD, TOOM, false, false>(tabs, m, q, r, s, st, claim, hoff);
