@@ -143,7 +143,10 @@ struct WarpChunks {  // 32-bit chunk ids: tables of up to 2^37 items
     __device__ __forceinline__ uint32_t cn() const { return DYN ? cn_dyn : c + gridDim.x * kWarps; }
     __device__ __forceinline__ static bool live(uint32_t chunk, uint64_t q) { return (uint64_t)chunk * 32 < q; }
     __device__ __forceinline__ void request(const ReduceArgs& ra, int lane) {  // top of a chunk: ask for the chunk after next
-        if (DYN && lane == 0) fetched = atomicAdd(ra.ticket + kWorkCounterOffset, 1u);
+        // inline PTX: nvcc turns a plain atomicAdd on a uniform address into a warp-aggregated one (ballot, leader, SHFL of
+        // the result), and that shuffle waits for the atomic right here instead of a chunk later (ncu: 2.3 % of the samples)
+        if (DYN && lane == 0)
+            asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(fetched) : "l"(ra.ticket + kWorkCounterOffset) : "memory");
     }
     __device__ __forceinline__ void advance() {  // bottom of a chunk (all lanes converged)
         if (DYN) {
@@ -228,7 +231,34 @@ __global__ void __launch_bounds__(kThreads, (D <= 1) ? (FOLD ? ZK_RK_MINBLOCKS_D
         wc.request(ra, lane);
         const uint64_t j = (uint64_t)wc.c * 32 + lane, jn = (uint64_t)wc.cn() * 32 + lane;
         const bool nvalid = jn < q;
-        if (j < q) {  // false only in the single ragged chunk of a table with fewer than 32 items
+        if constexpr (IMMA && TOOM) {
+            // Three factors, unrolled, every lane owns an item.  The first factor has no products to hide the next
+            // quadruple behind (ncu: 5.8 % of the samples waited for it at the head of the second fold), so table 1's
+            // quadruple is requested BEFORE the first fold, into registers the running products do not need yet; table 2's
+            // goes out before the second fold, the next item's first quadruple behind the last products as before.
+            Fe pr[D + 1], lo, hi;
+            Fe* const T0 = s_tab[0];
+            Fe* const T1 = s_tab[1];
+            Fe* const T2 = s_tab[2];
+            const Fe m0 = ld_fe_stream(T1 + j), m2 = ld_fe_stream(T1 + j + 2 * q), m1 = ld_fe_stream(T1 + j + q), m3 = ld_fe_stream(T1 + j + 3 * q);
+            // (prefetch.global.L2 of the next item's twelve rows a whole item ahead measured slower: 2.24 against 2.18 ms)
+            fold2(lo, hi, n0, n1, n2, n3, 0);
+            st_fe(T0 + j, lo);
+            st_fe(T0 + j + q, hi);
+            n0 = ld_fe_stream(T2 + j); n2 = ld_fe_stream(T2 + j + 2 * q); n1 = ld_fe_stream(T2 + j + q); n3 = ld_fe_stream(T2 + j + 3 * q);
+            item_terms<F, D, TOOM, IMMA>(0, false, true, lo, hi, pr, accw);
+            fold2(lo, hi, m0, m1, m2, m3, 0);
+            st_fe(T1 + j, lo);
+            st_fe(T1 + j + q, hi);
+            item_terms<F, D, TOOM, IMMA>(1, false, true, lo, hi, pr, accw);
+            fold2(lo, hi, n0, n1, n2, n3, 0);
+            st_fe(T2 + j, lo);
+            st_fe(T2 + j + q, hi);
+            if (nvalid) {
+                n0 = ld_fe_stream(T0 + jn); n2 = ld_fe_stream(T0 + jn + 2 * q); n1 = ld_fe_stream(T0 + jn + q); n3 = ld_fe_stream(T0 + jn + 3 * q);
+            }
+            item_terms<F, D, TOOM, IMMA>(2, true, true, lo, hi, pr, accw);
+        } else if (j < q) {  // false only in the single ragged chunk of a table with fewer than 32 items
             Fe pr[D + 1];
 #pragma unroll 1
             for (int k = 0; k < m; k++) {
