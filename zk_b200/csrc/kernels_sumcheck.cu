@@ -379,7 +379,7 @@ inline bool fold_on_f64(int m) {
     return forced >= 0 ? forced == 1 : m >= 2;
 }
 // The INT8 tensor path (fold_imma.cuh) for the degree-3, three-factor fused step with the claim known (the prover's
-// rounds): measured 2.36 ms against 2.44 ms (FP64 folds) for the first fused step of the 2^26 proof, bit-exact.
+// rounds): measured 2.18 ms against 2.44 ms (FP64 folds) for the first fused step of the 2^26 proof, bit-exact.
 // ZK_B200_FOLD_PIPE=imma2 (default: the two folds of an item staged together) | imma (one at a time: 2.52 ms) |
 // f64 | int (the other pipes).  Returns the kernel's FP parameter, 0 = off.
 inline int fold_on_imma() {
