@@ -20,6 +20,19 @@ def test_f64_fold_matches_host_multiplier(tmp_path):
     assert "4800000 checked" in out, out
 
 
+def test_tensor_path_fold_model_matches_host_field(tmp_path):
+    """The INT8 tensor-path fold (zk_b200/csrc/fold_imma.cuh): the real host table builder (fragment order) and a CPU
+    restatement of one warp's data flow (staging swizzle, ldmatrix.x4, mma.m16n8k32 fragment layouts, pair words, assembly,
+    one Montgomery row) against evaluation_form.rs:68 computed with the host field, both fields, extreme operands; also
+    asserts the bounds the exactness argument rests on (column sums < 2^21, pair words < 2^30)."""
+    exe = str(tmp_path / "test_fold_imma_host")
+    cmd = ["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "zk_b200", "csrc"),
+           os.path.join(ROOT, "tests", "cpp", "test_fold_imma_host.cpp"), "-o", exe]
+    subprocess.run(cmd, check=True, capture_output=True, timeout=300)
+    out = subprocess.run([exe], check=True, capture_output=True, timeout=300, text=True).stdout
+    assert "204800 checked, 0 mismatches" in out, out
+
+
 def test_keccak_avx512_matches_portable(tmp_path):
     """The AVX-512 absorb loop of the host transcript (zk_b200/csrc/keccak_avx512.cpp) against the portable
     Keccak-f[1600] of keccak.hpp: KATs, every length 0..1100 in six chunkings, large messages, digest chaining.
